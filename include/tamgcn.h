@@ -1,0 +1,180 @@
+/* tamgcn.h — C-ABI of the B200-native CTR-GCN / ST-GCN hot path (libtamgcn.so).
+ *
+ * The reference (Tamnemng/TAM-GCN) is pure Python/PyTorch and has no FFI of its own; the
+ * interface each entry point replaces is therefore the ATen call sequence inside the reference
+ * module named in its comment (paths relative to the reference checkout).  The Python host side
+ * (tam_gcn_b200/_C.py, ctypes) is the only caller; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types.  Every pointer is DEVICE memory owned by the caller
+ *    (the PyTorch caching allocator); the library never allocates, frees or keeps device memory.
+ *  - activations are contiguous planes (T, V) inside (N, C, T, V) tensors, V fastest.  A tensor
+ *    argument is (pointer to channel 0 of the slice, sample stride in ELEMENTS); channel stride is
+ *    always T*V.  This lets callers pass channel slices of wider tensors without copies.
+ *  - `dtype` selects the activation storage type: TAMGCN_F32 or TAMGCN_BF16.  Parameters, BN
+ *    coefficients and all gradients of parameters are fp32; BN statistics are fp64 accumulators.
+ *    All arithmetic accumulates in fp32.
+ *  - everything is enqueued on `stream` (a cudaStream_t), never synchronises, and is CUDA-graph
+ *    capturable.  Accumulator outputs (documented "+=") must be zeroed by the caller.
+ *  - return 0 on success, <0 on error; tamgcn_last_error() returns a thread-local message.
+ */
+#ifndef TAMGCN_H
+#define TAMGCN_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tamgcn_stream; /* cudaStream_t */
+
+enum { TAMGCN_F32 = 0, TAMGCN_BF16 = 1 };
+enum { TAMGCN_RES_NONE = 0, TAMGCN_RES_IDENTITY = 1, TAMGCN_RES_AFFINE = 2 };
+
+int tamgcn_version(void);
+const char* tamgcn_last_error(void);
+/* number of kernel launches issued by this library in the calling process (bench.py gpu_launches) */
+int64_t tamgcn_launch_count(void);
+
+/* A lazily transformed activation operand: value(n,ch,t,v) = f(a[ch]*P + b[ch]*Q + c[ch]),
+ * f = max(0,.) when relu != 0.  NULL a -> 1, NULL b (or NULL q) -> no Q term, NULL c -> 0.
+ * It is how BatchNorm-apply(+ReLU) (forward), the res - y difference of unit_gcn and the
+ * BatchNorm backward formula dY = A*dYhat + B*Y + C are fused into the consumer kernels. */
+typedef struct tamgcn_operand {
+    const void* p;
+    const void* q;
+    const float* a;
+    const float* b;
+    const float* c;
+    int64_t p_nstride;
+    int64_t q_nstride;
+    int32_t relu;
+    int32_t reserved;
+} tamgcn_operand;
+
+/* (k x 1) convolution geometry: nn.Conv2d(Cin, Cout, (k,1), stride (s,1), padding (pad,0), dilation (dil,1)) */
+typedef struct tamgcn_conv_geom {
+    int32_t N, Cin, Cout, T, To, V, k, stride, dil, pad;
+} tamgcn_conv_geom;
+
+/* ---- (k x 1) convolutions: models/ctrgcn.py:56-62,95-99,114,122,161-164,183-184,212,221;
+ *      models/stgcn.py:47-55,79,89 (nn.Conv2d forward / convolution_backward) ---------------------- */
+/* y[n,co,to,v] = bias[co] + sum_{ci,j} W[co,ci,j] * X(n,ci,to*s + j*dil - pad, v)   (zero padding)
+ * optional epilogue: per-channel sum / sum of squares of y over (n,to,v) for channels >= stat_c0
+ * (stat arrays indexed co - stat_c0, "+=").  W is (Cout,Cin,k) fp32. */
+int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* x, const float* W,
+                    const float* bias, void* y, int64_t y_nstride, double* stat_sum, double* stat_sumsq,
+                    int stat_c0, tamgcn_stream stream);
+/* dX = conv_transpose(dY) [+ addend] [+ bcast[n,ci,v]*bcast_scale];  if mask != NULL the result is
+ * multiplied by [mask.a*mask.P + mask.c > 0] (ReLU backward of the fused forward prologue) and
+ * s1[ci] += sum dX, s2[ci] += sum dX*mask.P (BatchNorm-backward reductions, may be NULL). */
+int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* dy, const float* W, void* dx,
+                      int64_t dx_nstride, const void* addend, int64_t addend_nstride, const float* bcast,
+                      float bcast_scale, const tamgcn_operand* mask, double* s1, double* s2,
+                      tamgcn_stream stream);
+/* dW[co,ci,j] += sum_{n,to,v} dY(n,co,to,v) * X(n,ci,to*s+j*dil-pad,v);  dbias[co] += sum dY (NULL to skip) */
+int tamgcn_conv_wgrad(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* dy, const tamgcn_operand* x,
+                      float* dW, float* dbias, tamgcn_stream stream);
+
+/* ---- CTRGC channel-wise topology refinement: models/ctrgcn.py:172-177 ---------------------------- */
+/* m[n,c,v] = mean_t x[n,c,t,v]  (fp32 out, (N,C,V)).  conv1/conv2 followed by .mean(-2) commute with the
+ * mean, so x1/x2 are produced by tamgcn_conv_fwd on m viewed as (N,Cin,T=1,V) with the stacked
+ * conv1/conv2 weights; their backward is tamgcn_conv_wgrad/dgrad on the same view plus the
+ * `bcast` term of tamgcn_conv_dgrad. */
+int tamgcn_mean_t(int dtype, const void* x, int64_t x_nstride, int N, int C, int T, int V, float* m,
+                  tamgcn_stream stream);
+/* y[n,c,t,u] = sum_i sum_v Q_i[n,c,u,v] * x3[n,i*Cout+c,t,v],
+ * Q_i[n,c,u,v] = alpha*(sum_r W4[i,c,r]*tanh(x1[n,i,r,u]-x2[n,i,r,v]) + b4[i,c]) + PA[i,u,v].
+ * x1,x2: fp32 (K,R,V) blocks per sample with sample stride x12_nstride; W4 (K,Cout,R); b4 (K,Cout);
+ * PA (K,V,V); alpha: device pointer to one float.  The (N,C,V,V) topology tensor lives in shared
+ * memory only.  Optional BN statistics of y ("+=").  V must be 20 or 25. */
+int tamgcn_ctrgc_fwd(int dtype, const void* x3, int64_t x3_nstride, int N, int Cout, int T, int V, int K, int R,
+                     const float* x1, const float* x2, int64_t x12_nstride, const float* W4, const float* b4,
+                     const float* PA, const float* alpha, void* y, int64_t y_nstride, double* stat_sum,
+                     double* stat_sumsq, tamgcn_stream stream);
+/* backward of the above for cotangent g (a lazy operand): dx3 (same layout as x3), and "+=" into
+ * dx1,dx2 (same layout as x1,x2), dW4 (K,Cout,R), db4 (K,Cout), dPA (K,V,V), dalpha (1). */
+int tamgcn_ctrgc_bwd(int dtype, const tamgcn_operand* g, const void* x3, int64_t x3_nstride, int N, int Cout, int T,
+                     int V, int K, int R, const float* x1, const float* x2, int64_t x12_nstride, const float* W4,
+                     const float* b4, const float* PA, const float* alpha, void* dx3, int64_t dx3_nstride,
+                     float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha,
+                     tamgcn_stream stream);
+
+/* ---- BatchNorm (nn.BatchNorm2d defaults, models/ctrgcn.py:64,100,115,118,123,186,213,222,230) ---- */
+typedef struct tamgcn_bn {
+    const double* sum;    /* batch statistics accumulated by a producer epilogue (train) */
+    const double* sumsq;
+    const float* gamma;   /* NULL -> 1 */
+    const float* beta;    /* NULL -> 0 */
+    float* rmean;         /* running stats: updated in train, read in eval */
+    float* rvar;
+    int64_t* nbt;         /* num_batches_tracked (+1 in train), may be NULL */
+    float* scale;         /* out: gamma*invstd */
+    float* shift;         /* out: beta - mean*scale */
+    float* mean;          /* out: mean used for normalisation */
+    float* invstd;        /* out */
+    int32_t C;
+    int32_t reserved;
+} tamgcn_bn;
+/* up to 8 BatchNorms per launch */
+int tamgcn_bn_finalize(int n_bn, const tamgcn_bn* bns, double count, float momentum, float eps, int train,
+                       tamgcn_stream stream);
+typedef struct tamgcn_bn_bwd {
+    const double* s1;     /* sum dYhat */
+    const double* s2;     /* sum dYhat * Y(raw) */
+    const float* gamma;   /* NULL -> 1 */
+    const float* mean;
+    const float* invstd;
+    float* A;             /* out: dY = A*dYhat + B*Y + C */
+    float* B;
+    float* Cc;
+    float* dgamma;        /* out (=, not +=), may be NULL */
+    float* dbeta;
+    int32_t C;
+    int32_t reserved;
+} tamgcn_bn_bwd;
+int tamgcn_bn_bwd_coef(int n_bn, const tamgcn_bn_bwd* bns, double count, int train, tamgcn_stream stream);
+
+/* ---- fused epilogues (BN + tanh/ReLU + residual): models/ctrgcn.py:255-261,145-146,283; stgcn.py:98-99 */
+/* out = relu( sg*y0+hg + tanh(so*z+ho) + res );  res = 0 | r | sr*r+hr */
+int tamgcn_gcn_epilogue_fwd(int dtype, int N, int C, int TV, const void* y0, const float* sg, const float* hg,
+                            const void* z, const float* so, const float* ho, int res_mode, const void* r,
+                            int64_t r_nstride, const float* sr, const float* hr, void* out, tamgcn_stream stream);
+/* G = g*[out>0];  DZ = G*(1-tanh(so*z+ho)^2);  s1o += sum DZ;  s2o += sum DZ*z */
+int tamgcn_gcn_epilogue_bwd(int dtype, int N, int C, int TV, const void* g, const void* out, const void* z,
+                            const float* so, const float* ho, void* G, void* DZ, double* s1o, double* s2o,
+                            tamgcn_stream stream);
+/* DY = G - DD (in place over G);  DR = G + DD (to dr, may be NULL);  s1g += sum DY; s2g += sum DY*y0;
+ * s1d += sum DR; s2d += sum DR*r (r, s1d, s2d may be NULL) */
+int tamgcn_gcn_mid_bwd(int dtype, int N, int C, int TV, void* G, const void* DD, void* dr, int64_t dr_nstride,
+                       const void* y0, const void* r, int64_t r_nstride, double* s1g, double* s2g, double* s1d,
+                       double* s2d, tamgcn_stream stream);
+/* out = f( su*u+hu + res ), f = relu if relu else identity */
+int tamgcn_tcn_epilogue_fwd(int dtype, int N, int C, int TV, const void* u, int64_t u_nstride, const float* su,
+                            const float* hu, int res_mode, const void* r, int64_t r_nstride, const float* sr,
+                            const float* hr, int relu, void* out, tamgcn_stream stream);
+/* G = relu ? g*[out>0] : g (G may be NULL when relu==0);  s1 += sum G; s2u += sum G*u; s2r += sum G*r */
+int tamgcn_tcn_epilogue_bwd(int dtype, int N, int C, int TV, const void* g, const void* out, int relu, const void* u,
+                            int64_t u_nstride, const void* r, int64_t r_nstride, void* G, double* s1, double* s2u,
+                            double* s2r, tamgcn_stream stream);
+/* MaxPool2d((3,1), stride (s,1), padding (1,0)) over the lazy operand x; optional BN stats of y */
+int tamgcn_maxpool_fwd(int dtype, int N, int C, int T, int To, int V, int stride, const tamgcn_operand* x, void* y,
+                       int64_t y_nstride, double* stat_sum, double* stat_sumsq, tamgcn_stream stream);
+/* dh = (sum over windows whose first arg-max is t of dY) * [x.a*x.P + x.c > 0];  s1 += sum dh; s2 += sum dh*x.P */
+int tamgcn_maxpool_bwd(int dtype, int N, int C, int T, int To, int V, int stride, const tamgcn_operand* dy,
+                       const tamgcn_operand* x, void* dh, int64_t dh_nstride, double* s1, double* s2,
+                       tamgcn_stream stream);
+
+/* ---- ST-GCN graph aggregation: models/stgcn.py:60-62  einsum('nkctv,kvw->nctw') -------------------- */
+int tamgcn_graph_agg_fwd(int dtype, int N, int K, int C, int T, int V, const void* y, int64_t y_nstride,
+                         const float* A, void* out, int64_t out_nstride, double* stat_sum, double* stat_sumsq,
+                         tamgcn_stream stream);
+/* dy[n,k*C+c,t,v] = sum_w dOut(n,c,t,w) A[k,v,w];  dA[k,v,w] += sum_{n,c,t} y[n,k*C+c,t,v] dOut(n,c,t,w) */
+int tamgcn_graph_agg_bwd(int dtype, int N, int K, int C, int T, int V, const tamgcn_operand* dout, const void* y,
+                         int64_t y_nstride, const float* A, void* dy, int64_t dy_nstride, float* dA,
+                         tamgcn_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAMGCN_H */

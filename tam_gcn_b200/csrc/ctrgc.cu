@@ -1,0 +1,388 @@
+// ctrgc.cu — fused CTRGC channel-wise topology refinement (reference models/ctrgcn.py:172-177).
+//
+//   D_i[n,r,u,v] = tanh(x1_i[n,r,u] - x2_i[n,r,v])
+//   Q_i[n,c,u,v] = alpha * (sum_r W4_i[c,r] D_i[n,r,u,v] + b4_i[c]) + PA_i[u,v]
+//   y[n,c,t,u]   = sum_i sum_v Q_i[n,c,u,v] * x3_i[n,c,t,v]
+//
+// One CTA owns one sample n and a tile of CT output channels.  D and Q (the N x C x V x V topology
+// tensor of the reference) exist only in shared memory; the CTA then streams the K*CT contiguous
+// (T x V) planes of x3 once and writes the CT planes of y once.  The sum over the K subsets and the
+// BatchNorm statistics of y are accumulated in the same pass.  The backward kernel recomputes D and
+// Q, streams g and x3 once, writes dx3 once and reduces dQ in shared memory into dPA, dalpha,
+// dW4, db4 and (through tanh') dx1, dx2.
+//
+// SIMT fp32 math for both storage types.  V is a template parameter (20 = NW-UCLA, 25 = NTU).
+#include "common.cuh"
+#include "rows.cuh"
+
+namespace tamgcn {
+
+// ---- mean over T (conv1/conv2 commute with it: conv(x).mean(-2) == conv(x.mean(-2))) --------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+mean_t_kernel(const T* __restrict__ x, long long xns, int C, int Tn, int V, float* __restrict__ m) {
+    const int n = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + w;
+    if (c >= C) return;
+    const T* px = x + (long long)n * xns + (long long)c * Tn * V;
+    const float inv = 1.f / (float)Tn;
+    for (int v = lane; v < V; v += 32) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int t = 0;
+        for (; t + 3 < Tn; t += 4) {
+            s0 += ldf<T>(px + (t + 0) * V + v);
+            s1 += ldf<T>(px + (t + 1) * V + v);
+            s2 += ldf<T>(px + (t + 2) * V + v);
+            s3 += ldf<T>(px + (t + 3) * V + v);
+        }
+        for (; t < Tn; ++t) s0 += ldf<T>(px + t * V + v);
+        m[((long long)n * C + c) * V + v] = ((s0 + s1) + (s2 + s3)) * inv;
+    }
+}
+
+struct CtrgcP {
+    int N, Cout, T, K, R, CT;
+    long long x3ns, x12ns, yns;
+};
+
+// D_i -> shared (pitch DP); also used by the backward kernel
+template <int V, int DP>
+__device__ __forceinline__ void build_D(float* Ds, const float* __restrict__ x1, const float* __restrict__ x2, int R) {
+    for (int idx = threadIdx.x; idx < R * V * V; idx += blockDim.x) {
+        const int r = idx / (V * V), rem = idx - r * V * V, u = rem / V, v = rem - u * V;
+        Ds[(r * V + u) * DP + v] = tanhf(__ldg(x1 + r * V + u) - __ldg(x2 + r * V + v));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+ctrgc_fwd_kernel(CtrgcP g, const T* __restrict__ x3, const float* __restrict__ x1, const float* __restrict__ x2,
+                 const float* __restrict__ W4, const float* __restrict__ b4, const float* __restrict__ PA,
+                 const float* __restrict__ alpha_p, T* __restrict__ y, double* ssum, double* ssq) {
+    constexpr int VP = VPad<V>::VP, DP = VPad<V>::DP;
+    extern __shared__ __align__(16) float smem[];
+    const int CT = g.CT, R = g.R, K = g.K;
+    float* Qs = smem;                          // [K][CT][V][VP]
+    float* Ds = Qs + K * CT * V * VP;          // [R][V][DP]
+    float* W4s = Ds + R * V * DP;              // [CT][R]
+    float* st = W4s + CT * R;                  // [CT][2]
+    const int n = blockIdx.y, c0 = blockIdx.x * CT;
+    const int nc = min(CT, g.Cout - c0);
+    const float alpha = __ldg(alpha_p);
+
+    for (int idx = threadIdx.x; idx < K * CT * V * VP; idx += blockDim.x) Qs[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < CT * 2; idx += blockDim.x) st[idx] = 0.f;
+
+    for (int i = 0; i < K; ++i) {
+        __syncthreads();
+        build_D<V, DP>(Ds, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
+        for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
+            W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nc * V * V; idx += blockDim.x) {
+            const int c = idx / (V * V), rem = idx - c * V * V, u = rem / V, v = rem - u * V;
+            float acc = __ldg(b4 + i * g.Cout + c0 + c);
+            const float* d = Ds + u * DP + v;
+            const float* w = W4s + c * R;
+            for (int r = 0; r < R; ++r) acc = fmaf(w[r], d[r * V * DP], acc);
+            Qs[((i * CT + c) * V + u) * VP + v] = fmaf(alpha, acc, __ldg(PA + (i * V + u) * V + v));
+        }
+    }
+    __syncthreads();
+
+    const int Tn = g.T;
+    for (int row = threadIdx.x; row < nc * Tn; row += blockDim.x) {
+        const int c = row / Tn, t = row - c * Tn;
+        float acc[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) acc[u] = 0.f;
+        for (int i = 0; i < K; ++i) {
+            float xr[VP];
+            load_row<T, V, VP>(x3 + (long long)n * g.x3ns + (((long long)i * g.Cout + c0 + c) * Tn + t) * V, xr);
+            const float* q = Qs + (i * CT + c) * V * VP;
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                float s = acc[u];
+#pragma unroll
+                for (int v4 = 0; v4 < VP / 4; ++v4) {
+                    const float4 qq = *reinterpret_cast<const float4*>(q + u * VP + 4 * v4);
+                    s = fmaf(qq.x, xr[4 * v4], s);
+                    s = fmaf(qq.y, xr[4 * v4 + 1], s);
+                    s = fmaf(qq.z, xr[4 * v4 + 2], s);
+                    s = fmaf(qq.w, xr[4 * v4 + 3], s);
+                }
+                acc[u] = s;
+            }
+        }
+        float s = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            acc[u] = rnd<T>(acc[u]);
+            s += acc[u];
+            q2 = fmaf(acc[u], acc[u], q2);
+        }
+        store_row<T, V>(y + (long long)n * g.yns + ((long long)(c0 + c) * Tn + t) * V, acc);
+        if (ssum) {
+            atomicAdd(&st[2 * c], s);
+            atomicAdd(&st[2 * c + 1], q2);
+        }
+    }
+    if (ssum) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+            atomicAdd(ssum + c0 + c, (double)st[2 * c]);
+            atomicAdd(ssq + c0 + c, (double)st[2 * c + 1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+ctrgc_bwd_kernel(CtrgcP g, Opnd go, const T* __restrict__ x3, const float* __restrict__ x1,
+                 const float* __restrict__ x2, const float* __restrict__ W4, const float* __restrict__ b4,
+                 const float* __restrict__ PA, const float* __restrict__ alpha_p, T* __restrict__ dx3,
+                 long long dx3ns, float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha) {
+    constexpr int VP = VPad<V>::VP, DP = VPad<V>::DP;
+    extern __shared__ __align__(16) float smem[];
+    const int CT = g.CT, R = g.R, K = g.K, Tn = g.T;
+    float* Qs = smem;                  // [CT][V][VP]
+    float* P4s = Qs + CT * V * VP;     // [CT][V][DP]   W4.D + b4
+    float* dQs = P4s + CT * V * DP;    // [CT][V][DP]
+    float* Ds = dQs + CT * V * DP;     // [R][V][DP]
+    float* W4s = Ds + R * V * DP;      // [CT][R]
+    float* red = W4s + CT * R;         // [64]
+    const int n = blockIdx.y, c0 = blockIdx.x * CT;
+    const int nc = min(CT, g.Cout - c0);
+    const float alpha = __ldg(alpha_p);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int TV = Tn * V;
+
+    for (int idx = threadIdx.x; idx < CT * V * VP; idx += blockDim.x) Qs[idx] = 0.f;
+    float dalpha_acc = 0.f;
+
+    for (int i = 0; i < K; ++i) {
+        __syncthreads();
+        build_D<V, DP>(Ds, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
+        for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
+            W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nc * V * V; idx += blockDim.x) {
+            const int c = idx / (V * V), rem = idx - c * V * V, u = rem / V, v = rem - u * V;
+            float acc = __ldg(b4 + i * g.Cout + c0 + c);
+            const float* d = Ds + u * DP + v;
+            const float* w = W4s + c * R;
+            for (int r = 0; r < R; ++r) acc = fmaf(w[r], d[r * V * DP], acc);
+            P4s[(c * V + u) * DP + v] = acc;
+            Qs[(c * V + u) * VP + v] = fmaf(alpha, acc, __ldg(PA + (i * V + u) * V + v));
+        }
+        __syncthreads();
+
+        // (a) dx3_i[c,t,v] = sum_u Q[c,u,v] g[c,t,u]
+        for (int row = threadIdx.x; row < nc * Tn; row += blockDim.x) {
+            const int c = row / Tn, t = row - c * Tn;
+            const OpCoef cf = opnd_coef(go, c0 + c);
+            const long long off = (long long)(c0 + c) * TV + t * V;
+            float acc[VP];
+#pragma unroll
+            for (int v = 0; v < VP; ++v) acc[v] = 0.f;
+            const float* q = Qs + c * V * VP;
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                const float gu = opnd_val<T>(go, cf, n, off + u);
+#pragma unroll
+                for (int v4 = 0; v4 < VP / 4; ++v4) {
+                    const float4 qq = *reinterpret_cast<const float4*>(q + u * VP + 4 * v4);
+                    acc[4 * v4] = fmaf(qq.x, gu, acc[4 * v4]);
+                    acc[4 * v4 + 1] = fmaf(qq.y, gu, acc[4 * v4 + 1]);
+                    acc[4 * v4 + 2] = fmaf(qq.z, gu, acc[4 * v4 + 2]);
+                    acc[4 * v4 + 3] = fmaf(qq.w, gu, acc[4 * v4 + 3]);
+                }
+            }
+            store_row<T, V>(dx3 + (long long)n * dx3ns + (((long long)i * g.Cout + c0 + c) * Tn + t) * V, acc);
+        }
+        // (b) dQ[c,u,v] = sum_t g[c,t,u] x3_i[c,t,v]     one thread per (c,u)
+        for (int task = threadIdx.x; task < nc * V; task += blockDim.x) {
+            const int c = task / V, u = task - c * V;
+            const OpCoef cf = opnd_coef(go, c0 + c);
+            const long long goff = (long long)(c0 + c) * TV + u;
+            const T* px = x3 + (long long)n * g.x3ns + ((long long)i * g.Cout + c0 + c) * TV;
+            float acc[VP];
+#pragma unroll
+            for (int v = 0; v < VP; ++v) acc[v] = 0.f;
+            for (int t = 0; t < Tn; ++t) {
+                const float gu = opnd_val<T>(go, cf, n, goff + t * V);
+                float xr[VP];
+                load_row<T, V, VP>(px + t * V, xr);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = fmaf(gu, xr[v], acc[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) dQs[(c * V + u) * DP + v] = acc[v];
+        }
+        __syncthreads();
+
+        // dPA_i[u,v] += sum_c dQ ;  dalpha += sum dQ * P4
+        for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
+            const int u = idx / V, v = idx - u * V;
+            float s = 0.f;
+            for (int c = 0; c < nc; ++c) {
+                const float dq = dQs[(c * V + u) * DP + v];
+                s += dq;
+                dalpha_acc = fmaf(dq, P4s[(c * V + u) * DP + v], dalpha_acc);
+            }
+            atomicAdd(dPA + (i * V + u) * V + v, s);
+        }
+        // db4_i[c] += alpha * sum_uv dQ ;  dW4_i[c,r] += alpha * sum_uv dQ[c,u,v] D[r,u,v]   (warp per task)
+        for (int task = warp; task < nc * (R + 1); task += nwarp) {
+            const int c = task / (R + 1), r = task - c * (R + 1);
+            float s = 0.f;
+            for (int idx = lane; idx < V * V; idx += 32) {
+                const int u = idx / V, v = idx - u * V;
+                const float dq = dQs[(c * V + u) * DP + v];
+                s += (r < R) ? dq * Ds[(r * V + u) * DP + v] : dq;
+            }
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (r < R) atomicAdd(dW4 + ((long long)i * g.Cout + c0 + c) * R + r, alpha * s);
+                else atomicAdd(db4 + i * g.Cout + c0 + c, alpha * s);
+            }
+        }
+        // dD[r,u,v] = alpha sum_c W4[c,r] dQ[c,u,v];  dS = dD (1 - D^2);  dx1[r,u] += sum_v dS;  dx2[r,v] -= sum_u dS
+        for (int task = threadIdx.x; task < 2 * R * V; task += blockDim.x) {
+            const int which = task / (R * V), rem = task - which * R * V, r = rem / V, w = rem - r * V;
+            float s = 0.f;
+            for (int o = 0; o < V; ++o) {
+                const int u = which ? o : w, v = which ? w : o;
+                float dd = 0.f;
+                for (int c = 0; c < nc; ++c) dd = fmaf(W4s[c * R + r], dQs[(c * V + u) * DP + v], dd);
+                const float dv = Ds[(r * V + u) * DP + v];
+                s = fmaf(dd, 1.f - dv * dv, s);
+            }
+            s *= alpha;
+            float* dst = (which ? dx2 : dx1) + (long long)n * g.x12ns + (i * R + r) * V + w;
+            atomicAdd(dst, which ? -s : s);
+        }
+    }
+    // dalpha
+    float dv[1] = {dalpha_acc};
+    block_sum<1>(dv, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha, dv[0]);
+}
+
+template <typename T>
+static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, const float* x2, const float* W4,
+                      const float* b4, const float* PA, const float* alpha, void* y, double* ssum, double* ssq,
+                      cudaStream_t st) {
+    dim3 grid(cdiv(g.Cout, g.CT), g.N);
+    if (V == 20) {
+        constexpr int VP = VPad<20>::VP, DP = VPad<20>::DP;
+        const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 20 * VP + (size_t)g.R * 20 * DP + g.CT * g.R + g.CT * 2);
+        TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
+        cudaFuncSetAttribute(ctrgc_fwd_kernel<T, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        ctrgc_fwd_kernel<T, 20><<<grid, 256, sm, st>>>(g, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)y, ssum, ssq);
+    } else {
+        constexpr int VP = VPad<25>::VP, DP = VPad<25>::DP;
+        const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 25 * VP + (size_t)g.R * 25 * DP + g.CT * g.R + g.CT * 2);
+        TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
+        cudaFuncSetAttribute(ctrgc_fwd_kernel<T, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        ctrgc_fwd_kernel<T, 25><<<grid, 256, sm, st>>>(g, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)y, ssum, ssq);
+    }
+    count_launch();
+    return check_launch("ctrgc_fwd");
+}
+
+template <typename T>
+static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, const float* x1, const float* x2,
+                      const float* W4, const float* b4, const float* PA, const float* alpha, void* dx3,
+                      long long dx3ns, float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha,
+                      cudaStream_t st) {
+    dim3 grid(cdiv(g.Cout, g.CT), g.N);
+    if (V == 20) {
+        constexpr int VP = VPad<20>::VP, DP = VPad<20>::DP;
+        const size_t sm = sizeof(float) * ((size_t)g.CT * 20 * VP + 2 * (size_t)g.CT * 20 * DP + (size_t)g.R * 20 * DP +
+                                           g.CT * g.R + 64);
+        TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
+        cudaFuncSetAttribute(ctrgc_bwd_kernel<T, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        ctrgc_bwd_kernel<T, 20><<<grid, 256, sm, st>>>(g, go, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)dx3, dx3ns,
+                                                       dx1, dx2, dW4, db4, dPA, dalpha);
+    } else {
+        constexpr int VP = VPad<25>::VP, DP = VPad<25>::DP;
+        const size_t sm = sizeof(float) * ((size_t)g.CT * 25 * VP + 2 * (size_t)g.CT * 25 * DP + (size_t)g.R * 25 * DP +
+                                           g.CT * g.R + 64);
+        TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
+        cudaFuncSetAttribute(ctrgc_bwd_kernel<T, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        ctrgc_bwd_kernel<T, 25><<<grid, 256, sm, st>>>(g, go, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)dx3, dx3ns,
+                                                       dx1, dx2, dW4, db4, dPA, dalpha);
+    }
+    count_launch();
+    return check_launch("ctrgc_bwd");
+}
+
+}  // namespace tamgcn
+
+using namespace tamgcn;
+
+extern "C" int tamgcn_mean_t(int dtype, const void* x, int64_t x_nstride, int N, int C, int T, int V, float* m,
+                             tamgcn_stream stream) {
+    TG_REQUIRE(x && m && N > 0 && C > 0 && T > 0 && V > 0, "mean_t: bad arguments");
+    TG_REQUIRE(N <= 65535, "mean_t: N too large");
+    dim3 grid(cdiv(C, 8), N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_F32) mean_t_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_nstride, C, T, V, m);
+    else if (dtype == TAMGCN_BF16) mean_t_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, x_nstride, C, T, V, m);
+    else return set_error("mean_t: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("mean_t");
+}
+
+static int ctrgc_common(const char* who, int N, int Cout, int T, int V, int K, int R) {
+    TG_REQUIRE(N > 0 && Cout > 0 && T > 0 && K > 0 && R > 0, "%s: empty dimension", who);
+    TG_REQUIRE(V == 20 || V == 25, "%s: V=%d not supported (20 = NW-UCLA, 25 = NTU RGB+D)", who, V);
+    TG_REQUIRE(N <= 65535, "%s: N too large for one launch", who);
+    return 0;
+}
+
+extern "C" int tamgcn_ctrgc_fwd(int dtype, const void* x3, int64_t x3_nstride, int N, int Cout, int T, int V, int K,
+                                int R, const float* x1, const float* x2, int64_t x12_nstride, const float* W4,
+                                const float* b4, const float* PA, const float* alpha, void* y, int64_t y_nstride,
+                                double* stat_sum, double* stat_sumsq, tamgcn_stream stream) {
+    if (ctrgc_common("ctrgc_fwd", N, Cout, T, V, K, R)) return -1;
+    TG_REQUIRE(x3 && x1 && x2 && W4 && b4 && PA && alpha && y, "ctrgc_fwd: null pointer");
+    TG_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "ctrgc_fwd: stats must both be set");
+    CtrgcP g;
+    g.N = N; g.Cout = Cout; g.T = T; g.K = K; g.R = R;
+    g.CT = (V == 20) ? 16 : 8;
+    if (R > 16 && V == 25) g.CT = 4;
+    g.x3ns = x3_nstride; g.x12ns = x12_nstride; g.yns = y_nstride;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_F32) return launch_fwd<float>(g, V, x3, x1, x2, W4, b4, PA, alpha, y, stat_sum, stat_sumsq, st);
+    if (dtype == TAMGCN_BF16) return launch_fwd<bf16>(g, V, x3, x1, x2, W4, b4, PA, alpha, y, stat_sum, stat_sumsq, st);
+    return set_error("ctrgc_fwd: bad dtype %d", dtype);
+}
+
+extern "C" int tamgcn_ctrgc_bwd(int dtype, const tamgcn_operand* gop, const void* x3, int64_t x3_nstride, int N,
+                                int Cout, int T, int V, int K, int R, const float* x1, const float* x2,
+                                int64_t x12_nstride, const float* W4, const float* b4, const float* PA,
+                                const float* alpha, void* dx3, int64_t dx3_nstride, float* dx1, float* dx2,
+                                float* dW4, float* db4, float* dPA, float* dalpha, tamgcn_stream stream) {
+    if (ctrgc_common("ctrgc_bwd", N, Cout, T, V, K, R)) return -1;
+    TG_REQUIRE(gop && gop->p && x3 && x1 && x2 && W4 && b4 && PA && alpha && dx3 && dx1 && dx2 && dW4 && db4 && dPA &&
+                   dalpha, "ctrgc_bwd: null pointer");
+    CtrgcP g;
+    g.N = N; g.Cout = Cout; g.T = T; g.K = K; g.R = R;
+    g.CT = 8;
+    g.x3ns = x3_nstride; g.x12ns = x12_nstride; g.yns = 0;
+    const Opnd go = make_opnd(gop);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_F32)
+        return launch_bwd<float>(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
+    if (dtype == TAMGCN_BF16)
+        return launch_bwd<bf16>(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
+    return set_error("ctrgc_bwd: bad dtype %d", dtype);
+}

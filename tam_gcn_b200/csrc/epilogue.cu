@@ -1,0 +1,376 @@
+// epilogue.cu — fused BatchNorm-apply / tanh / ReLU / residual epilogues and their backward passes,
+// plus the (3x1) max-pool branch of MultiScale_TemporalConv.
+//
+// Every kernel here is a single streaming pass over (N, C, T*V) activations: HBM-bound.  A CTA owns
+// one channel (so the BatchNorm coefficients are scalars in registers and the BatchNorm-backward
+// sums stay in registers until one fp64 atomic per CTA) and strides over samples.
+//
+// reference: models/ctrgcn.py:255-261 (unit_gcn tail), :113-119 (max-pool branch), :145-146 (cat + res),
+//            :283 (TCN_GCN_unit tail); models/stgcn.py:98-99 (st_gcn tail).
+#include "common.cuh"
+
+namespace tamgcn {
+
+// grid = (C, NG): CTA (c, j) handles samples j, j+NG, ...
+static inline dim3 ew_grid(int N, int C) {
+    int ng = (148 * 8 + C - 1) / C;
+    if (ng > N) ng = N;
+    if (ng < 1) ng = 1;
+    if (ng > 65535) ng = 65535;
+    return dim3(C, ng);
+}
+
+template <int NV>
+__device__ __forceinline__ void flush_stats(float (&v)[NV], double* const (&dst)[NV], int c) {
+    __shared__ float scratch[NV * 32];
+    block_sum<NV>(v, scratch);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (dst[i]) atomicAdd(dst[i] + c, (double)v[i]);
+    }
+}
+
+// out = relu( sg*y0+hg + tanh(so*z+ho) + res )
+template <typename T>
+__global__ void __launch_bounds__(256)
+gcn_epilogue_fwd_kernel(int N, int C, int TV, const T* __restrict__ y0, const float* __restrict__ sg,
+                        const float* __restrict__ hg, const T* __restrict__ z, const float* __restrict__ so,
+                        const float* __restrict__ ho, int res_mode, const T* __restrict__ r, long long rns,
+                        const float* __restrict__ sr, const float* __restrict__ hr, T* __restrict__ out) {
+    const int c = blockIdx.x;
+    const float a_g = sg[c], b_g = hg[c], a_o = so[c], b_o = ho[c];
+    const float a_r = (res_mode == TAMGCN_RES_AFFINE) ? sr[c] : 1.f;
+    const float b_r = (res_mode == TAMGCN_RES_AFFINE) ? hr[c] : 0.f;
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const long long base = ((long long)n * C + c) * TV;
+        const T* pr = (res_mode != TAMGCN_RES_NONE) ? r + (long long)n * rns + (long long)c * TV : nullptr;
+        for (int e = threadIdx.x; e < TV; e += blockDim.x) {
+            float v = fmaf(a_g, ldf<T>(y0 + base + e), b_g) + tanhf(fmaf(a_o, ldf<T>(z + base + e), b_o));
+            if (pr) v += fmaf(a_r, ldf<T>(pr + e), b_r);
+            stf<T>(out + base + e, fmaxf(v, 0.f));
+        }
+    }
+}
+
+// G = g*[out>0];  DZ = G*(1-o^2), o = tanh(so*z+ho);  s1o += sum DZ;  s2o += sum DZ*z
+template <typename T>
+__global__ void __launch_bounds__(256)
+gcn_epilogue_bwd_kernel(int N, int C, int TV, const T* __restrict__ g, const T* __restrict__ out,
+                        const T* __restrict__ z, const float* __restrict__ so, const float* __restrict__ ho,
+                        T* __restrict__ G, T* __restrict__ DZ, double* s1o, double* s2o) {
+    const int c = blockIdx.x;
+    const float a_o = so[c], b_o = ho[c];
+    float acc[2] = {0.f, 0.f};
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const long long base = ((long long)n * C + c) * TV;
+        for (int e = threadIdx.x; e < TV; e += blockDim.x) {
+            const float gv = (ldf<T>(out + base + e) > 0.f) ? ldf<T>(g + base + e) : 0.f;
+            const float zv = ldf<T>(z + base + e);
+            const float o = tanhf(fmaf(a_o, zv, b_o));
+            const float dz = rnd<T>(gv * (1.f - o * o));
+            stf<T>(G + base + e, gv);
+            stf<T>(DZ + base + e, dz);
+            acc[0] += dz;
+            acc[1] = fmaf(dz, zv, acc[1]);
+        }
+    }
+    double* const dst[2] = {s1o, s2o};
+    flush_stats<2>(acc, dst, c);
+}
+
+// DY = G - DD (in place over G);  DR = G + DD -> dr;  BN-backward sums for bn (y0) and down.bn (r)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gcn_mid_bwd_kernel(int N, int C, int TV, T* __restrict__ G, const T* __restrict__ DD, T* __restrict__ dr,
+                   long long drns, const T* __restrict__ y0, const T* __restrict__ r, long long rns, double* s1g,
+                   double* s2g, double* s1d, double* s2d) {
+    const int c = blockIdx.x;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const long long base = ((long long)n * C + c) * TV;
+        T* pdr = dr ? dr + (long long)n * drns + (long long)c * TV : nullptr;
+        const T* pr = r ? r + (long long)n * rns + (long long)c * TV : nullptr;
+        for (int e = threadIdx.x; e < TV; e += blockDim.x) {
+            const float gv = ldf<T>(G + base + e), dd = ldf<T>(DD + base + e);
+            const float dy = rnd<T>(gv - dd), drv = rnd<T>(gv + dd);
+            stf<T>(G + base + e, dy);
+            acc[0] += dy;
+            acc[1] = fmaf(dy, ldf<T>(y0 + base + e), acc[1]);
+            if (pdr) stf<T>(pdr + e, drv);
+            if (pr) {
+                acc[2] += drv;
+                acc[3] = fmaf(drv, ldf<T>(pr + e), acc[3]);
+            }
+        }
+    }
+    double* const dst[4] = {s1g, s2g, s1d, s2d};
+    flush_stats<4>(acc, dst, c);
+}
+
+// out = f( su*u+hu + res )
+template <typename T>
+__global__ void __launch_bounds__(256)
+tcn_epilogue_fwd_kernel(int N, int C, int TV, const T* __restrict__ u, long long uns, const float* __restrict__ su,
+                        const float* __restrict__ hu, int res_mode, const T* __restrict__ r, long long rns,
+                        const float* __restrict__ sr, const float* __restrict__ hr, int relu, T* __restrict__ out) {
+    const int c = blockIdx.x;
+    const float a_u = su[c], b_u = hu[c];
+    const float a_r = (res_mode == TAMGCN_RES_AFFINE) ? sr[c] : 1.f;
+    const float b_r = (res_mode == TAMGCN_RES_AFFINE) ? hr[c] : 0.f;
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const long long base = ((long long)n * C + c) * TV;
+        const T* pu = u + (long long)n * uns + (long long)c * TV;
+        const T* pr = (res_mode != TAMGCN_RES_NONE) ? r + (long long)n * rns + (long long)c * TV : nullptr;
+        for (int e = threadIdx.x; e < TV; e += blockDim.x) {
+            float v = fmaf(a_u, ldf<T>(pu + e), b_u);
+            if (pr) v += fmaf(a_r, ldf<T>(pr + e), b_r);
+            if (relu) v = fmaxf(v, 0.f);
+            stf<T>(out + base + e, v);
+        }
+    }
+}
+
+// G = relu ? g*[out>0] : g;  s1 += sum G;  s2u += sum G*u;  s2r += sum G*r
+template <typename T>
+__global__ void __launch_bounds__(256)
+tcn_epilogue_bwd_kernel(int N, int C, int TV, const T* __restrict__ g, const T* __restrict__ out, int relu,
+                        const T* __restrict__ u, long long uns, const T* __restrict__ r, long long rns,
+                        T* __restrict__ G, double* s1, double* s2u, double* s2r) {
+    const int c = blockIdx.x;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const long long base = ((long long)n * C + c) * TV;
+        const T* pu = u + (long long)n * uns + (long long)c * TV;
+        const T* pr = r ? r + (long long)n * rns + (long long)c * TV : nullptr;
+        for (int e = threadIdx.x; e < TV; e += blockDim.x) {
+            float gv = ldf<T>(g + base + e);
+            if (relu && !(ldf<T>(out + base + e) > 0.f)) gv = 0.f;
+            if (G) stf<T>(G + base + e, gv);
+            acc[0] += gv;
+            acc[1] = fmaf(gv, ldf<T>(pu + e), acc[1]);
+            if (pr) acc[2] = fmaf(gv, ldf<T>(pr + e), acc[2]);
+        }
+    }
+    double* const dst[3] = {s1, s2u, s2r};
+    flush_stats<3>(acc, dst, c);
+}
+
+// MaxPool2d((3,1), stride (s,1), padding (1,0)) over the lazily transformed input
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(int N, int C, int Tn, int To, int V, int s, Opnd x, T* __restrict__ y, long long yns, double* ssum,
+                   double* ssq) {
+    const int c = blockIdx.x;
+    const OpCoef cf = opnd_coef(x, c);
+    float acc[2] = {0.f, 0.f};
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        T* py = y + (long long)n * yns + (long long)c * To * V;
+        for (int e = threadIdx.x; e < To * V; e += blockDim.x) {
+            const int to = e / V, v = e - to * V;
+            float best = -INFINITY;
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt) {
+                const int t = to * s - 1 + dt;
+                if (t >= 0 && t < Tn) best = fmaxf(best, opnd_val<T>(x, cf, n, ((long long)c * Tn + t) * V + v));
+            }
+            best = rnd<T>(best);
+            stf<T>(py + e, best);
+            acc[0] += best;
+            acc[1] = fmaf(best, best, acc[1]);
+        }
+    }
+    double* const dst[2] = {ssum, ssq};
+    flush_stats<2>(acc, dst, c);
+}
+
+// dh[t] = [x.a*P+x.c > 0] * sum over windows `to` whose FIRST arg-max is t of dY(to)
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(int N, int C, int Tn, int To, int V, int s, Opnd dy, Opnd x, T* __restrict__ dh, long long dhns,
+                   double* s1, double* s2) {
+    const int c = blockIdx.x;
+    const OpCoef cf = opnd_coef(x, c), df = opnd_coef(dy, c);
+    float acc[2] = {0.f, 0.f};
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        T* pd = dh + (long long)n * dhns + (long long)c * Tn * V;
+        for (int e = threadIdx.x; e < Tn * V; e += blockDim.x) {
+            const int t = e / V, v = e - t * V;
+            const long long xoff = (long long)c * Tn * V;
+            const float pv = ldf<T>((const T*)x.p + (long long)n * x.pns + xoff + e);
+            float d = 0.f;
+            if (fmaf(cf.a, pv, cf.c) > 0.f) {
+                // windows containing t: to*s-1 <= t <= to*s+1
+                int to_lo = (t - 1 + s - 1) / s;  // ceil((t-1)/s), t-1 >= -1
+                if (t - 1 < 0) to_lo = 0;
+                const int to_hi = min(To - 1, (t + 1) / s);
+                for (int to = to_lo; to <= to_hi; ++to) {
+                    float best = -INFINITY;
+                    int arg = -1;
+#pragma unroll
+                    for (int dt = 0; dt < 3; ++dt) {
+                        const int tt = to * s - 1 + dt;
+                        if (tt >= 0 && tt < Tn) {
+                            const float val = opnd_val<T>(x, cf, n, xoff + (long long)tt * V + v);
+                            if (val > best) { best = val; arg = tt; }
+                        }
+                    }
+                    if (arg == t) d += opnd_val<T>(dy, df, n, ((long long)c * To + to) * V + v);
+                }
+            }
+            d = rnd<T>(d);
+            stf<T>(pd + e, d);
+            acc[0] += d;
+            acc[1] = fmaf(d, pv, acc[1]);
+        }
+    }
+    double* const dst[2] = {s1, s2};
+    flush_stats<2>(acc, dst, c);
+}
+
+}  // namespace tamgcn
+
+using namespace tamgcn;
+
+#define DISPATCH(dtype, who, KERNEL, grid, st, ...)                                        \
+    do {                                                                                   \
+        if ((dtype) == TAMGCN_F32) KERNEL<float><<<grid, 256, 0, st>>>(__VA_ARGS__);       \
+        else if ((dtype) == TAMGCN_BF16) KERNEL<bf16><<<grid, 256, 0, st>>>(__VA_ARGS__);  \
+        else return set_error(who ": bad dtype %d", (dtype));                              \
+        count_launch();                                                                    \
+        return check_launch(who);                                                          \
+    } while (0)
+
+#define TP(T_, p) ((T_*)(p))
+
+extern "C" int tamgcn_gcn_epilogue_fwd(int dtype, int N, int C, int TV, const void* y0, const float* sg,
+                                       const float* hg, const void* z, const float* so, const float* ho, int res_mode,
+                                       const void* r, int64_t r_nstride, const float* sr, const float* hr, void* out,
+                                       tamgcn_stream stream) {
+    TG_REQUIRE(N > 0 && C > 0 && TV > 0 && y0 && sg && hg && z && so && ho && out, "gcn_epilogue_fwd: bad arguments");
+    TG_REQUIRE(res_mode == TAMGCN_RES_NONE || r, "gcn_epilogue_fwd: residual tensor missing");
+    TG_REQUIRE(res_mode != TAMGCN_RES_AFFINE || (sr && hr), "gcn_epilogue_fwd: residual coefficients missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_F32)
+        gcn_epilogue_fwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)y0, sg, hg, (const float*)z, so, ho,
+                                                             res_mode, (const float*)r, r_nstride, sr, hr, (float*)out);
+    else if (dtype == TAMGCN_BF16)
+        gcn_epilogue_fwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)y0, sg, hg, (const bf16*)z, so, ho,
+                                                            res_mode, (const bf16*)r, r_nstride, sr, hr, (bf16*)out);
+    else return set_error("gcn_epilogue_fwd: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("gcn_epilogue_fwd");
+}
+
+extern "C" int tamgcn_gcn_epilogue_bwd(int dtype, int N, int C, int TV, const void* g, const void* out, const void* z,
+                                       const float* so, const float* ho, void* G, void* DZ, double* s1o, double* s2o,
+                                       tamgcn_stream stream) {
+    TG_REQUIRE(N > 0 && C > 0 && TV > 0 && g && out && z && so && ho && G && DZ && s1o && s2o,
+               "gcn_epilogue_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_F32)
+        gcn_epilogue_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)g, (const float*)out,
+                                                             (const float*)z, so, ho, (float*)G, (float*)DZ, s1o, s2o);
+    else if (dtype == TAMGCN_BF16)
+        gcn_epilogue_bwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)g, (const bf16*)out, (const bf16*)z,
+                                                            so, ho, (bf16*)G, (bf16*)DZ, s1o, s2o);
+    else return set_error("gcn_epilogue_bwd: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("gcn_epilogue_bwd");
+}
+
+extern "C" int tamgcn_gcn_mid_bwd(int dtype, int N, int C, int TV, void* G, const void* DD, void* dr,
+                                  int64_t dr_nstride, const void* y0, const void* r, int64_t r_nstride, double* s1g,
+                                  double* s2g, double* s1d, double* s2d, tamgcn_stream stream) {
+    TG_REQUIRE(N > 0 && C > 0 && TV > 0 && G && DD && y0 && s1g && s2g, "gcn_mid_bwd: bad arguments");
+    TG_REQUIRE(!r || (s1d && s2d), "gcn_mid_bwd: residual BN sums missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_F32)
+        gcn_mid_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (float*)G, (const float*)DD, (float*)dr, dr_nstride,
+                                                        (const float*)y0, (const float*)r, r_nstride, s1g, s2g, s1d, s2d);
+    else if (dtype == TAMGCN_BF16)
+        gcn_mid_bwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride,
+                                                       (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d);
+    else return set_error("gcn_mid_bwd: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("gcn_mid_bwd");
+}
+
+extern "C" int tamgcn_tcn_epilogue_fwd(int dtype, int N, int C, int TV, const void* u, int64_t u_nstride,
+                                       const float* su, const float* hu, int res_mode, const void* r,
+                                       int64_t r_nstride, const float* sr, const float* hr, int relu, void* out,
+                                       tamgcn_stream stream) {
+    TG_REQUIRE(N > 0 && C > 0 && TV > 0 && u && su && hu && out, "tcn_epilogue_fwd: bad arguments");
+    TG_REQUIRE(res_mode == TAMGCN_RES_NONE || r, "tcn_epilogue_fwd: residual tensor missing");
+    TG_REQUIRE(res_mode != TAMGCN_RES_AFFINE || (sr && hr), "tcn_epilogue_fwd: residual coefficients missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_F32)
+        tcn_epilogue_fwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)u, u_nstride, su, hu, res_mode,
+                                                             (const float*)r, r_nstride, sr, hr, relu, (float*)out);
+    else if (dtype == TAMGCN_BF16)
+        tcn_epilogue_fwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)u, u_nstride, su, hu, res_mode,
+                                                            (const bf16*)r, r_nstride, sr, hr, relu, (bf16*)out);
+    else return set_error("tcn_epilogue_fwd: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("tcn_epilogue_fwd");
+}
+
+extern "C" int tamgcn_tcn_epilogue_bwd(int dtype, int N, int C, int TV, const void* g, const void* out, int relu,
+                                       const void* u, int64_t u_nstride, const void* r, int64_t r_nstride, void* G,
+                                       double* s1, double* s2u, double* s2r, tamgcn_stream stream) {
+    TG_REQUIRE(N > 0 && C > 0 && TV > 0 && g && u && s1 && s2u, "tcn_epilogue_bwd: bad arguments");
+    TG_REQUIRE(!relu || (out && G), "tcn_epilogue_bwd: relu needs out and G");
+    TG_REQUIRE(!r || s2r, "tcn_epilogue_bwd: residual BN sum missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_F32)
+        tcn_epilogue_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)g, (const float*)out, relu,
+                                                             (const float*)u, u_nstride, (const float*)r, r_nstride,
+                                                             (float*)G, s1, s2u, s2r);
+    else if (dtype == TAMGCN_BF16)
+        tcn_epilogue_bwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)g, (const bf16*)out, relu,
+                                                            (const bf16*)u, u_nstride, (const bf16*)r, r_nstride,
+                                                            (bf16*)G, s1, s2u, s2r);
+    else return set_error("tcn_epilogue_bwd: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("tcn_epilogue_bwd");
+}
+
+extern "C" int tamgcn_maxpool_fwd(int dtype, int N, int C, int T, int To, int V, int stride, const tamgcn_operand* x,
+                                  void* y, int64_t y_nstride, double* stat_sum, double* stat_sumsq,
+                                  tamgcn_stream stream) {
+    TG_REQUIRE(N > 0 && C > 0 && T > 0 && V > 0 && stride >= 1 && x && x->p && y, "maxpool_fwd: bad arguments");
+    TG_REQUIRE(To == (T + 2 - 3) / stride + 1, "maxpool_fwd: To=%d inconsistent with T=%d stride=%d", To, T, stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = ew_grid(N, C);
+    const Opnd xo = make_opnd(x);
+    if (dtype == TAMGCN_F32)
+        maxpool_fwd_kernel<float><<<grid, 256, 0, st>>>(N, C, T, To, V, stride, xo, (float*)y, y_nstride, stat_sum, stat_sumsq);
+    else if (dtype == TAMGCN_BF16)
+        maxpool_fwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, T, To, V, stride, xo, (bf16*)y, y_nstride, stat_sum, stat_sumsq);
+    else return set_error("maxpool_fwd: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("maxpool_fwd");
+}
+
+extern "C" int tamgcn_maxpool_bwd(int dtype, int N, int C, int T, int To, int V, int stride, const tamgcn_operand* dy,
+                                  const tamgcn_operand* x, void* dh, int64_t dh_nstride, double* s1, double* s2,
+                                  tamgcn_stream stream) {
+    TG_REQUIRE(N > 0 && C > 0 && T > 0 && V > 0 && stride >= 1 && dy && dy->p && x && x->p && dh,
+               "maxpool_bwd: bad arguments");
+    TG_REQUIRE(To == (T + 2 - 3) / stride + 1, "maxpool_bwd: To=%d inconsistent with T=%d stride=%d", To, T, stride);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid = ew_grid(N, C);
+    const Opnd xo = make_opnd(x), dyo = make_opnd(dy);
+    if (dtype == TAMGCN_F32)
+        maxpool_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, T, To, V, stride, dyo, xo, (float*)dh, dh_nstride, s1, s2);
+    else if (dtype == TAMGCN_BF16)
+        maxpool_bwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, T, To, V, stride, dyo, xo, (bf16*)dh, dh_nstride, s1, s2);
+    else return set_error("maxpool_bwd: bad dtype %d", dtype);
+    count_launch();
+    return check_launch("maxpool_bwd");
+}

@@ -1,0 +1,348 @@
+"""Tensor-level wrappers over the C-ABI (one Python function per entry point of include/tamgcn.h).
+
+Everything here is a thin marshalling layer: it derives pointers / sizes / strides from torch CUDA
+tensors and enqueues the kernel on torch's current stream.  No arithmetic happens in Python and there
+is no fallback path — a missing library or a CPU tensor raises.
+
+Activation arguments may be channel-slice VIEWS of wider contiguous (N, C, T, V) tensors; the sample
+stride is taken from `stride(0)`.
+"""
+import ctypes as C
+
+import torch
+
+from . import _C
+
+RES_NONE, RES_IDENTITY, RES_AFFINE = _C.RES_NONE, _C.RES_IDENTITY, _C.RES_AFFINE
+
+
+class Opnd:
+    """Lazy operand  f(a[ch]*p + b[ch]*q + c[ch])  (see tamgcn_operand in include/tamgcn.h)."""
+    __slots__ = ('p', 'q', 'a', 'b', 'c', 'relu')
+
+    def __init__(self, p, q=None, a=None, b=None, c=None, relu=False):
+        self.p, self.q, self.a, self.b, self.c, self.relu = p, q, a, b, c, relu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return _C.F32
+    if t.dtype == torch.bfloat16:
+        return _C.BF16
+    raise TypeError('activation dtype %s not supported (float32 or bfloat16)' % t.dtype)
+
+
+def _act(t, dtype=None):
+    """(pointer, sample stride) of an (N, C, T, V) activation view with contiguous (T, V) planes."""
+    if not t.is_cuda:
+        raise RuntimeError('tam_gcn_b200 kernels need CUDA tensors (there is no CPU path)')
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError('mixed activation dtypes: %s vs %s' % (t.dtype, dtype))
+    N, Cc, T, V = t.shape
+    s = t.stride()
+    ok = (V == 1 or s[3] == 1) and (T == 1 or s[2] == V) and (Cc == 1 or s[1] == T * V)
+    if not ok:
+        raise ValueError('activation view must have contiguous (T,V) planes and channel stride T*V; '
+                         'got shape %s strides %s' % (tuple(t.shape), s))
+    return t.data_ptr(), (s[0] if N > 1 else Cc * T * V)
+
+
+def _f32(t, n=None):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+        raise TypeError('expected a contiguous CUDA float32 tensor')
+    if n is not None and t.numel() != n:
+        raise ValueError('expected %d elements, got %d' % (n, t.numel()))
+    return t.data_ptr()
+
+
+def _f64(t, n=None):
+    if t is None:
+        return None
+    if t.dtype != torch.float64 or not t.is_contiguous() or not t.is_cuda:
+        raise TypeError('expected a contiguous CUDA float64 tensor')
+    if n is not None and t.numel() != n:
+        raise ValueError('expected %d elements, got %d' % (n, t.numel()))
+    return t.data_ptr()
+
+
+def _operand(o, nch):
+    if torch.is_tensor(o):
+        o = Opnd(o)
+    dtype = o.p.dtype
+    p, pns = _act(o.p)
+    s = _C.Operand()
+    s.p, s.p_nstride = p, pns
+    if o.q is not None:
+        if o.q.shape != o.p.shape:
+            raise ValueError('operand p/q shape mismatch')
+        s.q, s.q_nstride = _act(o.q, dtype)
+    s.a, s.b, s.c = _f32(o.a, nch if o.a is not None else None), _f32(o.b, nch if o.b is not None else None), \
+        _f32(o.c, nch if o.c is not None else None)
+    s.relu = 1 if o.relu else 0
+    return s
+
+
+def _geom(N, Cin, Cout, T, To, V, k, stride, dil, pad):
+    g = _C.ConvGeom()
+    g.N, g.Cin, g.Cout, g.T, g.To, g.V, g.k, g.stride, g.dil, g.pad = N, Cin, Cout, T, To, V, k, stride, dil, pad
+    return g
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0):
+    """y = conv_{k x 1}(X) (+bias); optional (sum, sumsq) fp64 statistics of y for channels >= stat_c0."""
+    xp = x.p if isinstance(x, Opnd) else x
+    N, Cin, T, V = xp.shape
+    _, Cout, To, _ = y.shape
+    g = _geom(N, Cin, Cout, T, To, V, k, stride, dil, pad)
+    xo = _operand(x, Cin)
+    yp, yns = _act(y, xp.dtype)
+    ssum = ssq = None
+    if stats is not None:
+        ssum, ssq = _f64(stats[0], Cout - stat_c0), _f64(stats[1], Cout - stat_c0)
+    _C.check(_C.lib().tamgcn_conv_fwd(C.byref(g), _dt(xp), C.byref(xo), _f32(W, Cout * Cin * k), _f32(bias), yp, yns,
+                                      ssum, ssq, stat_c0, _stream()), 'tamgcn_conv_fwd')
+
+
+def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, bcast_scale=0.0, mask=None,
+               stats=None):
+    """dx = conv_transpose(dY) (+addend) (+bcast*scale); optional ReLU mask + BN-backward sums."""
+    dyp = dy.p if isinstance(dy, Opnd) else dy
+    N, Cout, To, V = dyp.shape
+    _, Cin, T, _ = dx.shape
+    g = _geom(N, Cin, Cout, T, To, V, k, stride, dil, pad)
+    dyo = _operand(dy, Cout)
+    dxp, dxns = _act(dx, dyp.dtype)
+    ap = ans = None
+    if addend is not None:
+        if addend.shape != dx.shape:
+            raise ValueError('addend shape mismatch')
+        ap, ans = _act(addend, dyp.dtype)
+    mo = None
+    if mask is not None:
+        if mask.p.shape != dx.shape:
+            raise ValueError('mask shape mismatch')
+        mo = C.byref(_operand(mask, Cin))
+    s1 = s2 = None
+    if stats is not None:
+        s1, s2 = _f64(stats[0], Cin), _f64(stats[1], Cin)
+    _C.check(_C.lib().tamgcn_conv_dgrad(C.byref(g), _dt(dyp), C.byref(dyo), _f32(W, Cout * Cin * k), dxp, dxns, ap,
+                                        ans or 0, _f32(bcast, N * Cin * V if bcast is not None else None),
+                                        float(bcast_scale), mo, s1, s2, _stream()), 'tamgcn_conv_dgrad')
+
+
+def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
+    """dW += dY (*) X, dbias += sum dY  (fp32 accumulators, zeroed by the caller)."""
+    dyp = dy.p if isinstance(dy, Opnd) else dy
+    xp = x.p if isinstance(x, Opnd) else x
+    N, Cout, To, V = dyp.shape
+    _, Cin, T, _ = xp.shape
+    g = _geom(N, Cin, Cout, T, To, V, k, stride, dil, pad)
+    dyo, xo = _operand(dy, Cout), _operand(x, Cin)
+    if xp.dtype != dyp.dtype:
+        raise TypeError('conv_wgrad: mixed activation dtypes')
+    _C.check(_C.lib().tamgcn_conv_wgrad(C.byref(g), _dt(dyp), C.byref(dyo), C.byref(xo), _f32(dW, Cout * Cin * k),
+                                        _f32(dbias, Cout if dbias is not None else None), _stream()),
+             'tamgcn_conv_wgrad')
+
+
+def mean_t(x, m):
+    """m[n,c,0,v] = mean_t x[n,c,t,v]; m is fp32 (N,C,1,V)."""
+    N, Cc, T, V = x.shape
+    xp, xns = _act(x)
+    _C.check(_C.lib().tamgcn_mean_t(_dt(x), xp, xns, N, Cc, T, V, _f32(m, N * Cc * V), _stream()), 'tamgcn_mean_t')
+
+
+def ctrgc_fwd(x3, x1, x2, W4, b4, PA, alpha, y, stats=None):
+    """Fused CTRGC forward.  x3: (N,K*Cout,T,V); x1,x2: fp32 (N,K*R,1,V) views; y: (N,Cout,T,V)."""
+    N, KC, T, V = x3.shape
+    K = PA.shape[0]
+    Cout = KC // K
+    R = x1.shape[1] // K
+    x3p, x3ns = _act(x3)
+    yp, yns = _act(y, x3.dtype)
+    x1p, x12ns = _act(x1, torch.float32)
+    x2p, x12ns2 = _act(x2, torch.float32)
+    assert x12ns == x12ns2
+    ssum = ssq = None
+    if stats is not None:
+        ssum, ssq = _f64(stats[0], Cout), _f64(stats[1], Cout)
+    _C.check(_C.lib().tamgcn_ctrgc_fwd(_dt(x3), x3p, x3ns, N, Cout, T, V, K, R, x1p, x2p, x12ns,
+                                       _f32(W4, K * Cout * R), _f32(b4, K * Cout), _f32(PA, K * V * V),
+                                       _f32(alpha, 1), yp, yns, ssum, ssq, _stream()), 'tamgcn_ctrgc_fwd')
+
+
+def ctrgc_bwd(g, x3, x1, x2, W4, b4, PA, alpha, dx3, dx1, dx2, dW4, db4, dPA, dalpha):
+    """Fused CTRGC backward (dx3 written; dx1, dx2, dW4, db4, dPA, dalpha accumulated)."""
+    N, KC, T, V = x3.shape
+    K = PA.shape[0]
+    Cout = KC // K
+    R = x1.shape[1] // K
+    go = _operand(g, Cout)
+    x3p, x3ns = _act(x3)
+    dx3p, dx3ns = _act(dx3, x3.dtype)
+    x1p, x12ns = _act(x1, torch.float32)
+    x2p, _ = _act(x2, torch.float32)
+    d1p, d12ns = _act(dx1, torch.float32)
+    d2p, _ = _act(dx2, torch.float32)
+    assert d12ns == x12ns
+    _C.check(_C.lib().tamgcn_ctrgc_bwd(_dt(x3), C.byref(go), x3p, x3ns, N, Cout, T, V, K, R, x1p, x2p, x12ns,
+                                       _f32(W4, K * Cout * R), _f32(b4, K * Cout), _f32(PA, K * V * V),
+                                       _f32(alpha, 1), dx3p, dx3ns, d1p, d2p, _f32(dW4, K * Cout * R),
+                                       _f32(db4, K * Cout), _f32(dPA, K * V * V), _f32(dalpha, 1), _stream()),
+             'tamgcn_ctrgc_bwd')
+
+
+def bn_finalize(descs, count, momentum, eps, train):
+    """descs: list of dicts with keys sum, sumsq, gamma, beta, rmean, rvar, nbt, scale, shift, mean, invstd."""
+    for i in range(0, len(descs), 8):
+        chunk = descs[i:i + 8]
+        arr = (_C.BnDesc * len(chunk))()
+        for s, d in zip(arr, chunk):
+            Cn = d['scale'].numel()
+            s.sum, s.sumsq = _f64(d.get('sum'), Cn if d.get('sum') is not None else None), \
+                _f64(d.get('sumsq'), Cn if d.get('sumsq') is not None else None)
+            s.gamma, s.beta = _p(d.get('gamma')), _p(d.get('beta'))
+            s.rmean, s.rvar, s.nbt = _p(d.get('rmean')), _p(d.get('rvar')), _p(d.get('nbt'))
+            s.scale, s.shift = _f32(d['scale'], Cn), _f32(d['shift'], Cn)
+            s.mean, s.invstd = _f32(d.get('mean'), Cn if d.get('mean') is not None else None), \
+                _f32(d.get('invstd'), Cn if d.get('invstd') is not None else None)
+            s.C = Cn
+        _C.check(_C.lib().tamgcn_bn_finalize(len(chunk), arr, float(count), float(momentum), float(eps),
+                                             1 if train else 0, _stream()), 'tamgcn_bn_finalize')
+
+
+def bn_bwd_coef(descs, count, train):
+    """descs: list of dicts with keys s1, s2, gamma, mean, invstd, A, B, Cc, dgamma, dbeta."""
+    for i in range(0, len(descs), 8):
+        chunk = descs[i:i + 8]
+        arr = (_C.BnBwdDesc * len(chunk))()
+        for s, d in zip(arr, chunk):
+            Cn = d['A'].numel()
+            s.s1, s.s2 = _f64(d['s1'], Cn), _f64(d['s2'], Cn)
+            s.gamma, s.mean, s.invstd = _p(d.get('gamma')), _f32(d['mean'], Cn), _f32(d['invstd'], Cn)
+            s.A, s.B, s.Cc = _f32(d['A'], Cn), _f32(d['B'], Cn), _f32(d['Cc'], Cn)
+            s.dgamma, s.dbeta = _p(d.get('dgamma')), _p(d.get('dbeta'))
+            s.C = Cn
+        _C.check(_C.lib().tamgcn_bn_bwd_coef(len(chunk), arr, float(count), 1 if train else 0, _stream()),
+                 'tamgcn_bn_bwd_coef')
+
+
+def _full(t, dtype):
+    if not t.is_contiguous() or t.dtype != dtype or not t.is_cuda:
+        raise TypeError('expected a contiguous CUDA %s tensor' % dtype)
+    return t.data_ptr()
+
+
+def _res(res_mode, r, dtype):
+    if res_mode == RES_NONE or r is None:
+        return None, 0
+    return _act(r, dtype)
+
+
+def gcn_epilogue_fwd(y0, sg, hg, z, so, ho, res_mode, r, sr, hr, out):
+    N, Cc, T, V = y0.shape
+    dt = y0.dtype
+    rp, rns = _res(res_mode, r, dt)
+    _C.check(_C.lib().tamgcn_gcn_epilogue_fwd(_dt(y0), N, Cc, T * V, _full(y0, dt), _f32(sg, Cc), _f32(hg, Cc),
+                                              _full(z, dt), _f32(so, Cc), _f32(ho, Cc), res_mode, rp, rns, _f32(sr),
+                                              _f32(hr), _full(out, dt), _stream()), 'tamgcn_gcn_epilogue_fwd')
+
+
+def gcn_epilogue_bwd(g, out, z, so, ho, G, DZ, s1o, s2o):
+    N, Cc, T, V = g.shape
+    dt = g.dtype
+    _C.check(_C.lib().tamgcn_gcn_epilogue_bwd(_dt(g), N, Cc, T * V, _full(g, dt), _full(out, dt), _full(z, dt),
+                                              _f32(so, Cc), _f32(ho, Cc), _full(G, dt), _full(DZ, dt), _f64(s1o, Cc),
+                                              _f64(s2o, Cc), _stream()), 'tamgcn_gcn_epilogue_bwd')
+
+
+def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d):
+    N, Cc, T, V = G.shape
+    dt = G.dtype
+    drp, drns = (None, 0) if dr is None else _act(dr, dt)
+    rp, rns = (None, 0) if r is None else _act(r, dt)
+    _C.check(_C.lib().tamgcn_gcn_mid_bwd(_dt(G), N, Cc, T * V, _full(G, dt), _full(DD, dt), drp, drns, _full(y0, dt),
+                                         rp, rns, _f64(s1g, Cc), _f64(s2g, Cc), _f64(s1d), _f64(s2d), _stream()),
+             'tamgcn_gcn_mid_bwd')
+
+
+def tcn_epilogue_fwd(u, su, hu, res_mode, r, sr, hr, relu, out):
+    N, Cc, T, V = u.shape
+    dt = u.dtype
+    up, uns = _act(u)
+    rp, rns = _res(res_mode, r, dt)
+    _C.check(_C.lib().tamgcn_tcn_epilogue_fwd(_dt(u), N, Cc, T * V, up, uns, _f32(su, Cc), _f32(hu, Cc), res_mode, rp,
+                                              rns, _f32(sr), _f32(hr), 1 if relu else 0, _full(out, dt), _stream()),
+             'tamgcn_tcn_epilogue_fwd')
+
+
+def tcn_epilogue_bwd(g, out, relu, u, r, G, s1, s2u, s2r):
+    N, Cc, T, V = g.shape
+    dt = g.dtype
+    up, uns = _act(u, dt)
+    rp, rns = (None, 0) if r is None else _act(r, dt)
+    _C.check(_C.lib().tamgcn_tcn_epilogue_bwd(_dt(g), N, Cc, T * V, _full(g, dt), _p(out), 1 if relu else 0, up, uns,
+                                              rp, rns, _p(G), _f64(s1, Cc), _f64(s2u, Cc), _f64(s2r), _stream()),
+             'tamgcn_tcn_epilogue_bwd')
+
+
+def maxpool_fwd(x, y, stride, stats=None):
+    xp = x.p if isinstance(x, Opnd) else x
+    N, Cc, T, V = xp.shape
+    To = y.shape[2]
+    xo = _operand(x, Cc)
+    yp, yns = _act(y, xp.dtype)
+    ssum = ssq = None
+    if stats is not None:
+        ssum, ssq = _f64(stats[0], Cc), _f64(stats[1], Cc)
+    _C.check(_C.lib().tamgcn_maxpool_fwd(_dt(xp), N, Cc, T, To, V, stride, C.byref(xo), yp, yns, ssum, ssq,
+                                         _stream()), 'tamgcn_maxpool_fwd')
+
+
+def maxpool_bwd(dy, x, dh, stride, stats=None):
+    dyp = dy.p if isinstance(dy, Opnd) else dy
+    N, Cc, To, V = dyp.shape
+    T = x.p.shape[2]
+    dyo, xo = _operand(dy, Cc), _operand(x, Cc)
+    dhp, dhns = _act(dh, dyp.dtype)
+    s1 = s2 = None
+    if stats is not None:
+        s1, s2 = _f64(stats[0], Cc), _f64(stats[1], Cc)
+    _C.check(_C.lib().tamgcn_maxpool_bwd(_dt(dyp), N, Cc, T, To, V, stride, C.byref(dyo), C.byref(xo), dhp, dhns, s1,
+                                         s2, _stream()), 'tamgcn_maxpool_bwd')
+
+
+def graph_agg_fwd(y, A, out, stats=None):
+    """out[n,c,t,w] = sum_{k,v} y[n,k*C+c,t,v] A[k,v,w]."""
+    N, KC, T, V = y.shape
+    K = A.shape[0]
+    Cc = KC // K
+    yp, yns = _act(y)
+    op, ons = _act(out, y.dtype)
+    ssum = ssq = None
+    if stats is not None:
+        ssum, ssq = _f64(stats[0], Cc), _f64(stats[1], Cc)
+    _C.check(_C.lib().tamgcn_graph_agg_fwd(_dt(y), N, K, Cc, T, V, yp, yns, _f32(A, K * V * V), op, ons, ssum, ssq,
+                                           _stream()), 'tamgcn_graph_agg_fwd')
+
+
+def graph_agg_bwd(dout, y, A, dy, dA):
+    dp = dout.p if isinstance(dout, Opnd) else dout
+    N, Cc, T, V = dp.shape
+    K = A.shape[0]
+    do = _operand(dout, Cc)
+    yp, yns = _act(y, dp.dtype)
+    dyp, dyns = _act(dy, dp.dtype)
+    _C.check(_C.lib().tamgcn_graph_agg_bwd(_dt(dp), N, K, Cc, T, V, C.byref(do), yp, yns, _f32(A, K * V * V), dyp,
+                                           dyns, _f32(dA, K * V * V if dA is not None else None), _stream()),
+             'tamgcn_graph_agg_bwd')

@@ -1,0 +1,132 @@
+"""B200-native ST-GCN graph layers: drop-in replacements for the classes of the reference's models/stgcn.py.
+
+Same class names, constructor / forward signatures and state_dict keys as models/stgcn.py:37-252.
+`ConvTemporalGraphical` and `st_gcn` run on the fused kernels of `tam_gcn_b200.functional`; `Model`
+is the thin wrapper (data_bn, edge-importance weighting, pooling, 1x1 classifier).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as Fn
+from .ctrgcn import import_class
+
+
+class ConvTemporalGraphical(nn.Module):
+    """(t_k x 1) conv Cin -> K*Cout followed by einsum('nkctv,kvw->nctw') with the K-partition adjacency
+    (models/stgcn.py:37-63)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, t_kernel_size=1, t_stride=1, t_padding=0,
+                 t_dilation=1, bias=True):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.conv = nn.Conv2d(in_channels, out_channels * kernel_size, kernel_size=(t_kernel_size, 1),
+                              padding=(t_padding, 0), stride=(t_stride, 1), dilation=(t_dilation, 1), bias=bias)
+
+    def forward(self, x, A):
+        assert A.size(0) == self.kernel_size
+        return Fn.CtgFn.apply(x, A, self, self.conv.weight, self.conv.bias), A
+
+
+class st_gcn(nn.Module):
+    """Graph conv -> BN -> ReLU -> (k_t x 1) conv (stride) -> BN -> Dropout, + residual, ReLU
+    (models/stgcn.py:66-99), fused into a handful of kernels."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, dropout=0, residual=True):
+        super().__init__()
+        assert len(kernel_size) == 2
+        assert kernel_size[0] % 2 == 1
+        padding = ((kernel_size[0] - 1) // 2, 0)
+        self.gcn = ConvTemporalGraphical(in_channels, out_channels, kernel_size[1])
+        self.tcn = nn.Sequential(nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True),
+                                 nn.Conv2d(out_channels, out_channels, (kernel_size[0], 1), (stride, 1), padding),
+                                 nn.BatchNorm2d(out_channels), nn.Dropout(dropout, inplace=True))
+        self.dropout_p = dropout
+        if not residual:
+            self.res_kind = 'none'
+            self.residual = lambda x: 0
+        elif in_channels == out_channels and stride == 1:
+            self.res_kind = 'identity'
+            self.residual = lambda x: x
+        else:
+            self.res_kind = 'conv'
+            self.residual = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=(stride, 1)),
+                                          nn.BatchNorm2d(out_channels))
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x, A):
+        assert A.size(0) == self.gcn.kernel_size
+        if self.dropout_p and self.training:
+            raise NotImplementedError('st_gcn: dropout > 0 in training mode is not fused yet (reference default is 0)')
+        return Fn.StGcnFn.apply(x, A, self, *Fn.st_gcn_params(self)), A
+
+
+class Model(nn.Module):
+    """ST-GCN with learnable per-layer edge importance (models/stgcn.py:102-252)."""
+
+    def __init__(self, in_channels=3, num_class=4, num_point=20, num_person=1, graph=None, graph_args=dict(),
+                 edge_importance_weighting=True, dropout=0, **kwargs):
+        super().__init__()
+        if graph is None:
+            raise ValueError("Graph class must be specified")
+        Graph = import_class(graph) if isinstance(graph, str) else graph
+        self.graph = Graph(**graph_args)
+        A = torch.tensor(self.graph.A, dtype=torch.float32, requires_grad=False)
+        self.register_buffer('A', A)
+        ks = (9, A.size(0))
+        self.num_point = num_point
+        self.data_bn = nn.BatchNorm1d(num_person * in_channels * num_point)
+        chans = [(in_channels, 64, 1), (64, 64, 1), (64, 64, 1), (64, 64, 1), (64, 128, 2), (128, 128, 1),
+                 (128, 128, 1), (128, 256, 2), (256, 256, 1), (256, 256, 1)]
+        self.st_gcn_networks = nn.ModuleList(
+            [st_gcn(ci, co, ks, s, residual=(i > 0), **kwargs) for i, (ci, co, s) in enumerate(chans)])
+        if edge_importance_weighting:
+            self.edge_importance = nn.ParameterList([nn.Parameter(torch.ones(self.A.size()))
+                                                     for _ in self.st_gcn_networks])
+        else:
+            self.edge_importance = [1] * len(self.st_gcn_networks)
+        self.fcn = nn.Conv2d(256, num_class, kernel_size=1)
+        self.drop_out = nn.Dropout(dropout) if dropout else (lambda x: x)
+        self.act_dtype = None
+
+    def _trunk(self, x):
+        from . import get_act_dtype
+        if x.dim() == 3:
+            N, T, VC = x.shape
+            x = x.view(N, T, self.num_point, -1).permute(0, 3, 1, 2).contiguous().unsqueeze(-1)
+        N, C, T, V, M = x.size()
+        x = x.permute(0, 4, 3, 1, 2).contiguous().view(N * M, V * C, T)
+        x = self.data_bn(x)
+        x = x.view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)
+        dt = self.act_dtype or get_act_dtype()
+        if x.dtype != dt:
+            x = x.to(dt)
+        for gcn, importance in zip(self.st_gcn_networks, self.edge_importance):
+            x, _ = gcn(x, self.A * importance)
+        return x.float(), N, M
+
+    def forward(self, x):
+        x, N, M = self._trunk(x)
+        x = x.mean(dim=(2, 3), keepdim=True).view(N, M, -1, 1, 1).mean(dim=1)
+        x = self.drop_out(x)
+        x = self.fcn(x)
+        return x.view(x.size(0), -1)
+
+    def extract_feature(self, x):
+        x, N, M = self._trunk(x)
+        _, c, t, v = x.size()
+        feature = x.view(N, M, c, t, v).permute(0, 2, 3, 4, 1)
+        out = self.fcn(x)
+        output = out.view(N, M, -1, t, v).permute(0, 2, 3, 4, 1)
+        return output, feature
+
+    def get_edge_importance_per_joint(self):
+        """Per-joint score: sum of |incoming| + |outgoing| edge-importance mass over all layers and partitions,
+        normalised by its maximum (models/stgcn.py:227-252)."""
+        V = self.A.size(1)
+        score = np.zeros(V)
+        for imp in self.edge_importance:
+            w = imp.detach().cpu().numpy()
+            score += w.sum(axis=(0, 1)) + w.sum(axis=(0, 2))
+        return score / score.max()

@@ -1,0 +1,283 @@
+"""Pure-torch emulation of every function in tam_gcn_b200/ops.py  —  TEST INFRASTRUCTURE ONLY.
+
+Same signatures and in-place output conventions as the real wrappers, written with ATen ops (and
+torch autograd for the backward primitives).  Used two ways:
+
+  * on CPU (no GPU in the build container): tests monkeypatch `tam_gcn_b200.ops` with these functions
+    to check the host-side orchestration in tam_gcn_b200/functional.py (packing of parameters,
+    BatchNorm coefficient algebra, gradient routing) against the golden fixtures;
+  * on the GPU box: each CUDA kernel is compared against its emulation on the same random inputs
+    (tests/test_kernels_gpu.py).
+
+Nothing under tam_gcn_b200/ imports this file.
+"""
+import torch
+import torch.nn.functional as F
+
+RES_NONE, RES_IDENTITY, RES_AFFINE = 0, 1, 2
+
+
+class Opnd:
+    __slots__ = ('p', 'q', 'a', 'b', 'c', 'relu')
+
+    def __init__(self, p, q=None, a=None, b=None, c=None, relu=False):
+        self.p, self.q, self.a, self.b, self.c, self.relu = p, q, a, b, c, relu
+
+
+def _cv(t):
+    return t.view(1, -1, 1, 1)
+
+
+def val(o, dtype=torch.float32):
+    if torch.is_tensor(o):
+        return o.to(dtype)
+    v = o.p.to(dtype)
+    if o.a is not None:
+        v = v * _cv(o.a).to(dtype)
+    if o.q is not None and o.b is not None:
+        v = v + o.q.to(dtype) * _cv(o.b).to(dtype)
+    if o.c is not None:
+        v = v + _cv(o.c).to(dtype)
+    if o.relu:
+        v = torch.relu(v)
+    return v
+
+
+def _store(dst, v):
+    dst.copy_(v.to(dst.dtype))
+    return dst.to(torch.float32)
+
+
+def _acc(stat, v):
+    stat += v.double().sum((0, 2, 3))
+
+
+def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0):
+    xv = val(x)
+    Cout, Cin = y.shape[1], xv.shape[1]
+    out = F.conv2d(xv, W.reshape(Cout, Cin, k, 1), bias, stride=(stride, 1), padding=(pad, 0), dilation=(dil, 1))
+    out = _store(y, out)
+    if stats is not None:
+        _acc(stats[0], out[:, stat_c0:])
+        _acc(stats[1], out[:, stat_c0:] ** 2)
+
+
+def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, bcast_scale=0.0, mask=None,
+               stats=None):
+    dyv = val(dy)
+    N, Cin, T, V = dx.shape
+    Cout = dyv.shape[1]
+    g = torch.nn.grad.conv2d_input((N, Cin, T, V), W.reshape(Cout, Cin, k, 1), dyv, stride=(stride, 1),
+                                   padding=(pad, 0), dilation=(dil, 1))
+    if addend is not None:
+        g = g + addend.float()
+    if bcast is not None:
+        g = g + bcast.reshape(N, Cin, 1, V) * bcast_scale
+    if mask is not None:
+        pv = mask.p.float()
+        mv = pv * (_cv(mask.a) if mask.a is not None else 1.0) + (_cv(mask.c) if mask.c is not None else 0.0)
+        g = g * (mv > 0)
+        g = _store(dx, g)
+        if stats is not None:
+            _acc(stats[0], g)
+            _acc(stats[1], g * pv)
+    else:
+        _store(dx, g)
+
+
+def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
+    dyv, xv = val(dy), val(x)
+    Cout, Cin = dyv.shape[1], xv.shape[1]
+    g = torch.nn.grad.conv2d_weight(xv, (Cout, Cin, k, 1), dyv, stride=(stride, 1), padding=(pad, 0),
+                                    dilation=(dil, 1))
+    dW += g.reshape(dW.shape)
+    if dbias is not None:
+        dbias += dyv.sum((0, 2, 3))
+
+
+def mean_t(x, m):
+    m.copy_(x.float().mean(2, keepdim=True))
+
+
+def _ctrgc(x3, x1, x2, W4, b4, PA, alpha):
+    N, KC, T, V = x3.shape
+    K = PA.shape[0]
+    Cc = KC // K
+    R = x1.shape[1] // K
+    D = torch.tanh(x1.reshape(N, K, R, V, 1) - x2.reshape(N, K, R, 1, V))
+    Q = alpha.reshape(()) * (torch.einsum('kcr,nkruv->nkcuv', W4, D) + b4.view(1, K, Cc, 1, 1)) + PA.view(1, K, 1, V, V)
+    return torch.einsum('nkcuv,nkctv->nctu', Q, x3.reshape(N, K, Cc, T, V))
+
+
+def ctrgc_fwd(x3, x1, x2, W4, b4, PA, alpha, y, stats=None):
+    out = _store(y, _ctrgc(x3.float(), x1, x2, W4, b4, PA, alpha))
+    if stats is not None:
+        _acc(stats[0], out)
+        _acc(stats[1], out ** 2)
+
+
+def ctrgc_bwd(g, x3, x1, x2, W4, b4, PA, alpha, dx3, dx1, dx2, dW4, db4, dPA, dalpha):
+    with torch.enable_grad():
+        leaves = [t.detach().float().clone().requires_grad_(True) for t in (x3, x1, x2, W4, b4, PA, alpha)]
+        y = _ctrgc(*leaves)
+        gr = torch.autograd.grad(y, leaves, val(g))
+    dx3.copy_(gr[0].to(dx3.dtype))
+    dx1 += gr[1]
+    dx2 += gr[2]
+    dW4 += gr[3]
+    db4 += gr[4]
+    dPA += gr[5]
+    dalpha += gr[6].reshape(dalpha.shape)
+
+
+def bn_finalize(descs, count, momentum, eps, train):
+    for d in descs:
+        if train:
+            mean = d['sum'] / count
+            var = (d['sumsq'] / count - mean * mean).clamp_min(0)
+            if d.get('rmean') is not None:
+                unb = var * count / (count - 1) if count > 1 else var
+                d['rmean'].copy_(((1 - momentum) * d['rmean'].double() + momentum * mean).float())
+                d['rvar'].copy_(((1 - momentum) * d['rvar'].double() + momentum * unb).float())
+            if d.get('nbt') is not None:
+                d['nbt'] += 1
+        else:
+            mean, var = d['rmean'].double(), d['rvar'].double()
+        invstd = (1.0 / torch.sqrt(var + eps)).float()
+        gamma = d['gamma'] if d.get('gamma') is not None else torch.ones_like(invstd)
+        beta = d['beta'] if d.get('beta') is not None else torch.zeros_like(invstd)
+        scale = gamma * invstd
+        d['scale'].copy_(scale)
+        d['shift'].copy_(beta - mean.float() * scale)
+        if d.get('mean') is not None:
+            d['mean'].copy_(mean.float())
+        if d.get('invstd') is not None:
+            d['invstd'].copy_(invstd)
+
+
+def bn_bwd_coef(descs, count, train):
+    for d in descs:
+        mean, invstd = d['mean'].double(), d['invstd'].double()
+        s1, s2 = d['s1'], d['s2']
+        sx = invstd * (s2 - mean * s1)
+        gamma = d['gamma'].double() if d.get('gamma') is not None else torch.ones_like(mean)
+        A = gamma * invstd
+        if train:
+            B = -A * invstd * sx / count
+            Cc = -A * s1 / count - B * mean
+        else:
+            B = torch.zeros_like(A)
+            Cc = torch.zeros_like(A)
+        d['A'].copy_(A.float())
+        d['B'].copy_(B.float())
+        d['Cc'].copy_(Cc.float())
+        if d.get('dgamma') is not None:
+            d['dgamma'].copy_(sx.float())
+        if d.get('dbeta') is not None:
+            d['dbeta'].copy_(s1.float())
+
+
+def _resval(res_mode, r, sr, hr):
+    if res_mode == RES_NONE:
+        return 0.0
+    if res_mode == RES_IDENTITY:
+        return r.float()
+    return r.float() * _cv(sr) + _cv(hr)
+
+
+def gcn_epilogue_fwd(y0, sg, hg, z, so, ho, res_mode, r, sr, hr, out):
+    v = y0.float() * _cv(sg) + _cv(hg) + torch.tanh(z.float() * _cv(so) + _cv(ho)) + _resval(res_mode, r, sr, hr)
+    _store(out, torch.relu(v))
+
+
+def gcn_epilogue_bwd(g, out, z, so, ho, G, DZ, s1o, s2o):
+    gv = g.float() * (out.float() > 0)
+    o = torch.tanh(z.float() * _cv(so) + _cv(ho))
+    _store(G, gv)
+    dz = _store(DZ, gv * (1 - o * o))
+    _acc(s1o, dz)
+    _acc(s2o, dz * z.float())
+
+
+def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d):
+    gv, dd = G.float(), DD.float()
+    dy = (gv - dd).to(G.dtype).float()
+    drv = (gv + dd).to(G.dtype).float()
+    G.copy_(dy.to(G.dtype))
+    _acc(s1g, dy)
+    _acc(s2g, dy * y0.float())
+    if dr is not None:
+        dr.copy_(drv.to(dr.dtype))
+    if r is not None:
+        _acc(s1d, drv)
+        _acc(s2d, drv * r.float())
+
+
+def tcn_epilogue_fwd(u, su, hu, res_mode, r, sr, hr, relu, out):
+    v = u.float() * _cv(su) + _cv(hu) + _resval(res_mode, r, sr, hr)
+    _store(out, torch.relu(v) if relu else v)
+
+
+def tcn_epilogue_bwd(g, out, relu, u, r, G, s1, s2u, s2r):
+    gv = g.float()
+    if relu:
+        gv = gv * (out.float() > 0)
+    if G is not None:
+        G.copy_(gv.to(G.dtype))
+    _acc(s1, gv)
+    _acc(s2u, gv * u.float())
+    if r is not None:
+        _acc(s2r, gv * r.float())
+
+
+def maxpool_fwd(x, y, stride, stats=None):
+    out = _store(y, F.max_pool2d(val(x), (3, 1), (stride, 1), (1, 0)))
+    if stats is not None:
+        _acc(stats[0], out)
+        _acc(stats[1], out ** 2)
+
+
+def maxpool_bwd(dy, x, dh, stride, stats=None):
+    with torch.enable_grad():
+        xv = val(x).detach().requires_grad_(True)
+        y = F.max_pool2d(xv, (3, 1), (stride, 1), (1, 0))
+        g, = torch.autograd.grad(y, xv, val(dy))
+    pv = x.p.float()
+    mv = pv * (_cv(x.a) if x.a is not None else 1.0) + (_cv(x.c) if x.c is not None else 0.0)
+    g = _store(dh, g * (mv > 0))
+    if stats is not None:
+        _acc(stats[0], g)
+        _acc(stats[1], g * pv)
+
+
+def graph_agg_fwd(y, A, out, stats=None):
+    N, KC, T, V = y.shape
+    K = A.shape[0]
+    o = _store(out, torch.einsum('nkctv,kvw->nctw', y.float().reshape(N, K, KC // K, T, V), A))
+    if stats is not None:
+        _acc(stats[0], o)
+        _acc(stats[1], o ** 2)
+
+
+def graph_agg_bwd(dout, y, A, dy, dA):
+    gv = val(dout)
+    N, KC, T, V = y.shape
+    K = A.shape[0]
+    dy.copy_(torch.einsum('nctw,kvw->nkctv', gv, A).reshape(N, KC, T, V).to(dy.dtype))
+    if dA is not None:
+        dA += torch.einsum('nkctv,nctw->kvw', y.float().reshape(N, K, KC // K, T, V), gv)
+
+
+ALL = ['conv_fwd', 'conv_dgrad', 'conv_wgrad', 'mean_t', 'ctrgc_fwd', 'ctrgc_bwd', 'bn_finalize', 'bn_bwd_coef',
+       'gcn_epilogue_fwd', 'gcn_epilogue_bwd', 'gcn_mid_bwd', 'tcn_epilogue_fwd', 'tcn_epilogue_bwd', 'maxpool_fwd',
+       'maxpool_bwd', 'graph_agg_fwd', 'graph_agg_bwd']
+
+
+def install(monkeypatch):
+    """Route tam_gcn_b200.functional through the emulation (CPU orchestration tests)."""
+    import tam_gcn_b200.ops as real
+    import tam_gcn_b200.functional as Fn
+    g = globals()
+    for name in ALL:
+        monkeypatch.setattr(real, name, g[name])
+    monkeypatch.setattr(Fn, '_check_input', lambda x: x.contiguous())
