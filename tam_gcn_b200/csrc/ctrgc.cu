@@ -14,6 +14,7 @@
 // SIMT fp32 math for both storage types.  V is a template parameter (20 = NW-UCLA, 25 = NTU).
 #include "common.cuh"
 #include "rows.cuh"
+#include <atomic>
 
 namespace tamgcn {
 
@@ -275,6 +276,16 @@ ctrgc_bwd_kernel(CtrgcP g, Opnd go, const T* __restrict__ x3, const float* __res
     if (threadIdx.x == 0) atomicAdd(dalpha, dv[0]);
 }
 
+// raise the dynamic shared-memory limit of a kernel only when a larger size than ever before is needed
+// (warm-up calls do it; replays / CUDA-graph captures then issue no attribute call)
+template <typename K>
+static void ensure_smem(K kernel, std::atomic<int>& cur, size_t bytes) {
+    if ((int)bytes > cur.load(std::memory_order_relaxed)) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cur.store((int)bytes, std::memory_order_relaxed);
+    }
+}
+
 template <typename T>
 static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, const float* x2, const float* W4,
                       const float* b4, const float* PA, const float* alpha, void* y, double* ssum, double* ssq,
@@ -284,13 +295,15 @@ static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, c
         constexpr int VP = VPad<20>::VP, DP = VPad<20>::DP;
         const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 20 * VP + (size_t)g.R * 20 * DP + g.CT * g.R + g.CT * 2);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
-        cudaFuncSetAttribute(ctrgc_fwd_kernel<T, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        static std::atomic<int> cur{48 * 1024};
+        ensure_smem(ctrgc_fwd_kernel<T, 20>, cur, sm);
         ctrgc_fwd_kernel<T, 20><<<grid, 256, sm, st>>>(g, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)y, ssum, ssq);
     } else {
         constexpr int VP = VPad<25>::VP, DP = VPad<25>::DP;
         const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 25 * VP + (size_t)g.R * 25 * DP + g.CT * g.R + g.CT * 2);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
-        cudaFuncSetAttribute(ctrgc_fwd_kernel<T, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        static std::atomic<int> cur{48 * 1024};
+        ensure_smem(ctrgc_fwd_kernel<T, 25>, cur, sm);
         ctrgc_fwd_kernel<T, 25><<<grid, 256, sm, st>>>(g, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)y, ssum, ssq);
     }
     count_launch();
@@ -308,7 +321,8 @@ static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, co
         const size_t sm = sizeof(float) * ((size_t)g.CT * 20 * VP + 2 * (size_t)g.CT * 20 * DP + (size_t)g.R * 20 * DP +
                                            g.CT * g.R + 64);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
-        cudaFuncSetAttribute(ctrgc_bwd_kernel<T, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        static std::atomic<int> cur{48 * 1024};
+        ensure_smem(ctrgc_bwd_kernel<T, 20>, cur, sm);
         ctrgc_bwd_kernel<T, 20><<<grid, 256, sm, st>>>(g, go, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)dx3, dx3ns,
                                                        dx1, dx2, dW4, db4, dPA, dalpha);
     } else {
@@ -316,7 +330,8 @@ static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, co
         const size_t sm = sizeof(float) * ((size_t)g.CT * 25 * VP + 2 * (size_t)g.CT * 25 * DP + (size_t)g.R * 25 * DP +
                                            g.CT * g.R + 64);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
-        cudaFuncSetAttribute(ctrgc_bwd_kernel<T, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        static std::atomic<int> cur{48 * 1024};
+        ensure_smem(ctrgc_bwd_kernel<T, 25>, cur, sm);
         ctrgc_bwd_kernel<T, 25><<<grid, 256, sm, st>>>(g, go, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)dx3, dx3ns,
                                                        dx1, dx2, dW4, db4, dPA, dalpha);
     }

@@ -110,14 +110,16 @@ class Model(nn.Module):
         x, N, M = self._trunk(x)
         x = x.mean(dim=(2, 3), keepdim=True).view(N, M, -1, 1, 1).mean(dim=1)
         x = self.drop_out(x)
-        x = self.fcn(x)
-        return x.view(x.size(0), -1)
+        # 1x1 classifier on the pooled (N,256,1,1) feature == a linear layer (kept off cuDNN's TF32 default)
+        return F.linear(x.view(N, -1), self.fcn.weight.view(self.fcn.out_channels, -1), self.fcn.bias)
 
     def extract_feature(self, x):
         x, N, M = self._trunk(x)
         _, c, t, v = x.size()
         feature = x.view(N, M, c, t, v).permute(0, 2, 3, 4, 1)
-        out = self.fcn(x)
+        out = torch.einsum('oc,nctv->notv', self.fcn.weight.view(self.fcn.out_channels, -1), x)
+        if self.fcn.bias is not None:
+            out = out + self.fcn.bias.view(1, -1, 1, 1)
         output = out.view(N, M, -1, t, v).permute(0, 2, 3, 4, 1)
         return output, feature
 

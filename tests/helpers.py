@@ -89,7 +89,7 @@ def run_case(name, device='cpu', act_dtype=torch.float32):
     return dict(y=y.detach().float().cpu(), dx=x.grad.detach().float().cpu(), grads=grads, buffers=bufs)
 
 
-def compare(name, res, fx, tol_y, tol_dx, tol_g, tol_buf=None, report=None):
+def compare(name, res, fx, tol_y, tol_dx, tol_g, tol_buf=None, report=None, tol_gall=None):
     """Relative-L2 comparison against a golden fixture.  Returns the list of failures (strings)."""
     fails = []
     e_y, e_dx = O.rel_err(res['y'], fx['y']), O.rel_err(res['dx'], fx['dx'])
@@ -111,6 +111,13 @@ def compare(name, res, fx, tol_y, tol_dx, tol_g, tol_buf=None, report=None):
             worst_g, worst_k = e, k
         if not e <= tol_g:
             fails.append('%s: grad %s rel err %.3e > %.1e' % (name, k, e, tol_g))
+    if tol_gall is not None:
+        ks = [k for k in fx['grads'] if k in res['grads']]
+        ga = torch.cat([res['grads'][k].reshape(-1) for k in ks])
+        gb = torch.cat([fx['grads'][k].reshape(-1) for k in ks])
+        e = O.rel_err(ga, gb)
+        if not e <= tol_gall:
+            fails.append('%s: whole-gradient rel err %.3e > %.1e' % (name, e, tol_gall))
     worst_b = 0.0
     for k, b in fx['buffers'].items():
         if k not in res['buffers']:
