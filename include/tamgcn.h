@@ -59,17 +59,24 @@ typedef struct tamgcn_conv_geom {
 
 /* ---- (k x 1) convolutions: models/ctrgcn.py:56-62,95-99,114,122,161-164,183-184,212,221;
  *      models/stgcn.py:47-55,79,89 (nn.Conv2d forward / convolution_backward) ---------------------- */
+/* Tensor-core (tcgen05) path of the bf16 convolutions: the fp32 weights are first packed into bf16 tiles laid
+ * out exactly as the MMA reads them from shared memory (K-major, 128-byte swizzle), one buffer for the forward
+ * and one for the data-gradient GEMM.  `tamgcn_conv_pack_bytes` gives the buffer sizes; pass the buffers as
+ * `wpack` to tamgcn_conv_fwd / tamgcn_conv_dgrad.  wpack == NULL (or dtype F32) selects the exact-fp32 SIMT path. */
+int64_t tamgcn_conv_pack_bytes(int Cout, int Cin, int k, int dgrad);
+int tamgcn_conv_pack_weights(const float* W, int Cout, int Cin, int k, void* wpack_fwd, void* wpack_dgrad,
+                             tamgcn_stream stream);
 /* y[n,co,to,v] = bias[co] + sum_{ci,j} W[co,ci,j] * X(n,ci,to*s + j*dil - pad, v)   (zero padding)
  * optional epilogue: per-channel sum / sum of squares of y over (n,to,v) for channels >= stat_c0
  * (stat arrays indexed co - stat_c0, "+=").  W is (Cout,Cin,k) fp32. */
 int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* x, const float* W,
-                    const float* bias, void* y, int64_t y_nstride, double* stat_sum, double* stat_sumsq,
-                    int stat_c0, tamgcn_stream stream);
+                    const void* wpack, const float* bias, void* y, int64_t y_nstride, double* stat_sum,
+                    double* stat_sumsq, int stat_c0, tamgcn_stream stream);
 /* dX = conv_transpose(dY) [+ addend] [+ bcast[n,ci,v]*bcast_scale];  if mask != NULL the result is
  * multiplied by [mask.a*mask.P + mask.c > 0] (ReLU backward of the fused forward prologue) and
  * s1[ci] += sum dX, s2[ci] += sum dX*mask.P (BatchNorm-backward reductions, may be NULL). */
-int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* dy, const float* W, void* dx,
-                      int64_t dx_nstride, const void* addend, int64_t addend_nstride, const float* bcast,
+int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* dy, const float* W,
+                      const void* wpack, void* dx, int64_t dx_nstride, const void* addend, int64_t addend_nstride, const float* bcast,
                       float bcast_scale, const tamgcn_operand* mask, double* s1, double* s2,
                       tamgcn_stream stream);
 /* dW[co,ci,j] += sum_{n,to,v} dY(n,co,to,v) * X(n,ci,to*s+j*dil-pad,v);  dbias[co] += sum dY (NULL to skip) */

@@ -44,8 +44,9 @@ GEOM = C.POINTER(ConvGeom)
 
 # name -> argtypes; must list every entry point of include/tamgcn.h (tests/test_cabi.py checks this)
 SIGNATURES = {
-    'tamgcn_conv_fwd': [GEOM, i32, OP, vp, vp, vp, i64, vp, vp, i32, vp],
-    'tamgcn_conv_dgrad': [GEOM, i32, OP, vp, vp, i64, vp, i64, vp, f32, OP, vp, vp, vp],
+    'tamgcn_conv_pack_weights': [vp, i32, i32, i32, vp, vp, vp],
+    'tamgcn_conv_fwd': [GEOM, i32, OP, vp, vp, vp, vp, i64, vp, vp, i32, vp],
+    'tamgcn_conv_dgrad': [GEOM, i32, OP, vp, vp, vp, i64, vp, i64, vp, f32, OP, vp, vp, vp],
     'tamgcn_conv_wgrad': [GEOM, i32, OP, OP, vp, vp, vp],
     'tamgcn_mean_t': [i32, vp, i64, i32, i32, i32, i32, vp, vp],
     'tamgcn_ctrgc_fwd': [i32, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp],
@@ -78,6 +79,8 @@ def lib():
         l.tamgcn_version.restype = i32
         l.tamgcn_last_error.restype = C.c_char_p
         l.tamgcn_launch_count.restype = i64
+        l.tamgcn_conv_pack_bytes.restype = i64
+        l.tamgcn_conv_pack_bytes.argtypes = [i32, i32, i32, i32]
         for name, args in SIGNATURES.items():
             f = getattr(l, name)
             f.argtypes = args

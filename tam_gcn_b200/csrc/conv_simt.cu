@@ -329,15 +329,29 @@ static ConvP to_p(const tamgcn_conv_geom* g) {
 
 using namespace tamgcn;
 
+// tensor-core (tcgen05) paths, conv_tc.cu: return 1 if they handled the call, 0 to fall through, <0 on error
+namespace tamgcn {
+int conv_fwd_tc(const tamgcn_conv_geom* g, const Opnd& x, const void* wpack, const float* bias, void* y, long long yns,
+                double* ssum, double* ssq, int stat_c0, cudaStream_t st);
+int conv_dgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const void* wpack, void* dx, long long dxns,
+                  const void* addend, long long addns, const float* bcast, float bscale, const Opnd* mask, double* s1,
+                  double* s2, cudaStream_t st);
+int conv_wgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
+}
+
 extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* x, const float* W,
-                               const float* bias, void* y, int64_t y_nstride, double* stat_sum, double* stat_sumsq,
-                               int stat_c0, tamgcn_stream stream) {
+                               const void* wpack, const float* bias, void* y, int64_t y_nstride, double* stat_sum,
+                               double* stat_sumsq, int stat_c0, tamgcn_stream stream) {
     if (check_geom(g)) return -1;
     TG_REQUIRE(x && x->p && W && y, "conv_fwd: null pointer");
     TG_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "conv_fwd: stat_sum/stat_sumsq must both be set");
     const ConvP p = to_p(g);
     const Opnd xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_BF16) {
+        const int rc = conv_fwd_tc(g, xo, wpack, bias, y, y_nstride, stat_sum, stat_sumsq, stat_c0, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     dim3 grid(cdiv((long long)p.To * p.V, TN), cdiv(p.Cout, TM), p.N);
     if (dtype == TAMGCN_F32) {
         conv_fwd_kernel<float><<<grid, 256, 0, st>>>(p, xo, W, bias, (float*)y, y_nstride, stat_sum, stat_sumsq, stat_c0);
@@ -351,7 +365,7 @@ extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgc
 }
 
 extern "C" int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* dy, const float* W,
-                                 void* dx, int64_t dx_nstride, const void* addend, int64_t addend_nstride,
+                                 const void* wpack, void* dx, int64_t dx_nstride, const void* addend, int64_t addend_nstride,
                                  const float* bcast, float bcast_scale, const tamgcn_operand* mask, double* s1,
                                  double* s2, tamgcn_stream stream) {
     if (check_geom(g)) return -1;
@@ -364,6 +378,11 @@ extern "C" int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tam
     Opnd mo = plain_opnd(nullptr, 0);
     if (mask) mo = make_opnd(mask);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_BF16) {
+        const int rc = conv_dgrad_tc(g, dyo, wpack, dx, dx_nstride, addend, addend_nstride, bcast, bcast_scale,
+                                     mask ? &mo : nullptr, s1, s2, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     dim3 grid(cdiv((long long)p.T * p.V, TN), cdiv(p.Cin, TM), p.N);
     if (dtype == TAMGCN_F32) {
         conv_dgrad_kernel<float><<<grid, 256, 0, st>>>(p, dyo, W, (float*)dx, dx_nstride, (const float*)addend,
@@ -385,6 +404,10 @@ extern "C" int tamgcn_conv_wgrad(const tamgcn_conv_geom* g, int dtype, const tam
     const ConvP p = to_p(g);
     const Opnd dyo = make_opnd(dy), xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_BF16) {
+        const int rc = conv_wgrad_tc(g, dyo, xo, dW, dbias, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     const int gx = cdiv((long long)p.Cin * p.k, TN), gy = cdiv(p.Cout, TM);
     const int nblk = cdiv((long long)p.To * p.V, WG_BLK);
     const long long units = (long long)p.N * nblk;

@@ -54,6 +54,13 @@ def _w2(conv):
     return w.reshape(w.shape[0], -1)
 
 
+def _pack(W2d, k, like):
+    """Tensor-core weight tiles (wpack_fwd, wpack_dgrad) when activations are bf16; (None, None) in fp32 mode."""
+    if like.dtype != torch.bfloat16:
+        return None, None
+    return ops.conv_pack_weights(W2d, W2d.shape[0], W2d.shape[1] // k, k)
+
+
 def _bias(conv, like):
     if conv.bias is None:
         return torch.zeros(conv.weight.shape[0], device=like.device, dtype=torch.float32)
@@ -198,7 +205,9 @@ class UnitGcnFn(torch.autograd.Function):
         Cw = KC + (Cout if has_down else 0)
         xw = _empty((N, Cw, T, V), x)
         stats = _zeros((6, Cout), x, torch.float64) if train else None   # rows: down(sum,sq), bn(sum,sq), offset(sum,sq)
-        ops.conv_fwd(x, W3, b3, xw, stats=(stats[0], stats[1]) if (train and has_down) else None, stat_c0=KC)
+        pk3 = _pack(W3, 1, x)
+        ops.conv_fwd(x, W3, b3, xw, stats=(stats[0], stats[1]) if (train and has_down) else None, stat_c0=KC,
+                     wpack=pk3[0])
         # fused topology refinement + aggregation (+ BN statistics of y0)
         y0 = _empty((N, Cout, T, V), x)
         ops.ctrgc_fwd(xw[:, :KC], x12[:, :K * R], x12[:, K * R:], W4, b4, PA, alpha, y0,
@@ -228,7 +237,8 @@ class UnitGcnFn(torch.autograd.Function):
         oc = mod.offset_conv[0]
         Wo, bo = _w2(oc), _bias(oc, x)
         z = _empty((N, Cout, T, V), x)
-        ops.conv_fwd(diff, Wo, bo, z, stats=(stats[4], stats[5]) if train else None)
+        pko = _pack(Wo, 1, x)
+        ops.conv_fwd(diff, Wo, bo, z, stats=(stats[4], stats[5]) if train else None, wpack=pko[0])
         co = _BnCoef(Cout, x)
         _bn_forward([mod.offset_conv[1]], [_full(Cout)], co, (stats[4], stats[5]) if train else None, count, train)
         out = _empty((N, Cout, T, V), x)
@@ -238,7 +248,7 @@ class UnitGcnFn(torch.autograd.Function):
         ctx.res_mode = res_mode
         ctx.diff = diff
         ctx.coefs = (cg, cd, co)
-        ctx.packed = (W12, W3, W4, b4, PA, Wo)
+        ctx.packed = (W12, W3, W4, b4, PA, Wo, pk3[1], pko[1])
         ctx.save_for_backward(x, m, x12, xw, y0, z, out)
         return out
 
@@ -248,7 +258,7 @@ class UnitGcnFn(torch.autograd.Function):
         N, Cin, Cout, T, V, K, R = ctx.dims
         x, m, x12, xw, y0, z, out = ctx.saved_tensors
         cg, cd, co = ctx.coefs
-        W12, W3, W4, b4, PA, Wo = ctx.packed
+        W12, W3, W4, b4, PA, Wo, pk3d, pkod = ctx.packed
         has_down = cd is not None
         res_mode = ctx.res_mode
         KC, count = K * Cout, N * T * V
@@ -269,7 +279,7 @@ class UnitGcnFn(torch.autograd.Function):
         dbo = _zeros((Cout,), x, torch.float32)
         ops.conv_wgrad(dz, ctx.diff, dWo, dbo)
         DD = _empty(g.shape, x)
-        ops.conv_dgrad(dz, Wo, DD)
+        ops.conv_dgrad(dz, Wo, DD, wpack=pkod)
         # dY = G - DD (grad wrt bn output), dRes = G + DD; BN / down.BN backward sums
         Cw = xw.shape[1]
         dxw = _empty(xw.shape, x)
@@ -315,7 +325,7 @@ class UnitGcnFn(torch.autograd.Function):
         db3 = _zeros((Cw,), x, torch.float32)
         ops.conv_wgrad(dxw_op, x, dW3, db3)
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dxw_op, W3, dx, addend=dres, bcast=dm, bcast_scale=1.0 / T)
+        ops.conv_dgrad(dxw_op, W3, dx, addend=dres, bcast=dm, bcast_scale=1.0 / T, wpack=pk3d)
 
         grads = _ctrgc_unpack_grads(list(mod.convs), K, R, Cout, dW12, db12, dW3, db3, dW4, db4)
         if has_down:
@@ -347,11 +357,12 @@ class CtrgcFn(torch.autograd.Function):
         x12 = _empty((N, 2 * R, 1, V), x, torch.float32)
         ops.conv_fwd(m, W12, b12, x12)
         x3 = _empty((N, Cout, T, V), x)
-        ops.conv_fwd(x, W3, b3, x3)
+        pk3 = _pack(W3, 1, x)
+        ops.conv_fwd(x, W3, b3, x3, wpack=pk3[0])
         y = _empty((N, Cout, T, V), x)
         ops.ctrgc_fwd(x3, x12[:, :R], x12[:, R:], W4, b4, PA, al, y)
         ctx.mod, ctx.dims = mod, (N, Cin, Cout, T, V, R)
-        ctx.packed = (W12, W3, W4, b4, PA, al)
+        ctx.packed = (W12, W3, W4, b4, PA, al, pk3[1])
         ctx.save_for_backward(x, m, x12, x3)
         ctx.a_shape, ctx.alpha_shape = A.shape, alpha.shape
         return y
@@ -361,7 +372,7 @@ class CtrgcFn(torch.autograd.Function):
         mod = ctx.mod
         N, Cin, Cout, T, V, R = ctx.dims
         x, m, x12, x3 = ctx.saved_tensors
-        W12, W3, W4, b4, PA, al = ctx.packed
+        W12, W3, W4, b4, PA, al, pk3d = ctx.packed
         g = g.contiguous().to(x.dtype)
         dx3 = _empty(x3.shape, x)
         dx12 = _zeros(x12.shape, x, torch.float32)
@@ -380,7 +391,7 @@ class CtrgcFn(torch.autograd.Function):
         db3 = _zeros((Cout,), x, torch.float32)
         ops.conv_wgrad(dx3, x, dW3, db3)
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dx3, W3, dx, bcast=dm, bcast_scale=1.0 / T)
+        ops.conv_dgrad(dx3, W3, dx, bcast=dm, bcast_scale=1.0 / T, wpack=pk3d)
         grads = _ctrgc_unpack_grads([mod], 1, R, Cout, dW12, db12, dW3, db3, dW4, db4)
         return (dx, dPA.reshape(ctx.a_shape), dalpha.reshape(ctx.alpha_shape), None) + tuple(grads)
 
@@ -409,12 +420,13 @@ class ConvBnFn(torch.autograd.Function):
         W, b = _w2(conv), _bias(conv, x)
         raw = _empty((N, Cout, To, V), x)
         stats = _zeros((2, Cout), x, torch.float64) if train else None
-        ops.conv_fwd(x, W, b, raw, k, s, d, p, stats=stats)
+        pk = _pack(W, k, x)
+        ops.conv_fwd(x, W, b, raw, k, s, d, p, stats=stats, wpack=pk[0])
         cf = _BnCoef(Cout, x)
         _bn_forward([bn], [_full(Cout)], cf, stats, N * To * V, train)
         out = _empty(raw.shape, x)
         ops.tcn_epilogue_fwd(raw, cf.scale, cf.shift, RES_NONE, None, None, None, False, out)
-        ctx.conv, ctx.bn, ctx.train, ctx.geom, ctx.cf = conv, bn, train, (k, s, d, p), cf
+        ctx.conv, ctx.bn, ctx.train, ctx.geom, ctx.cf, ctx.pkd = conv, bn, train, (k, s, d, p), cf, pk[1]
         ctx.save_for_backward(x, raw)
         return out
 
@@ -435,7 +447,7 @@ class ConvBnFn(torch.autograd.Function):
         db = _zeros((Cout,), x, torch.float32)
         ops.conv_wgrad(dy, x, dW, db, k, s, d, p)
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dy, W, dx, k, s, d, p)
+        ops.conv_dgrad(dy, W, dx, k, s, d, p, wpack=ctx.pkd)
         return dx, None, None, dW.view_as(conv.weight), (db if conv.bias is not None else None), bw.dgamma, bw.dbeta
 
 
@@ -484,13 +496,16 @@ class MsTcnFn(torch.autograd.Function):
         bh = torch.cat([_bias(c, x) for c in heads])
         h = _empty((N, Ch, T, V), x)
         st_h = _zeros((2, Ch), x, torch.float64) if train else None
-        ops.conv_fwd(x, Wh, bh, h, stats=st_h)
+        pkh = _pack(Wh, 1, x)
+        ops.conv_fwd(x, Wh, bh, h, stats=st_h, wpack=pkh[0])
         u = _empty((N, Cout, To, V), x)
         st_u = _zeros((2, Cout), x, torch.float64) if train else None
         # strided 1x1 branch straight into its slice of u
         c3 = mod.branches[nd + 1][0]
         W3, b3 = _w2(c3), _bias(c3, x)
-        ops.conv_fwd(x, W3, b3, u[:, Ch:], 1, s, 1, 0, stats=(st_u[0][Ch:], st_u[1][Ch:]) if train else None)
+        pk3 = _pack(W3, 1, x)
+        ops.conv_fwd(x, W3, b3, u[:, Ch:], 1, s, 1, 0, stats=(st_u[0][Ch:], st_u[1][Ch:]) if train else None,
+                     wpack=pk3[0])
         ch = _BnCoef(Ch, x)
         sl = [slice(j * Cb, (j + 1) * Cb) for j in range(nb)]
         _bn_forward([mod.branches[j][1] for j in range(nd + 1)], sl[:nd + 1], ch, st_h, N * T * V, train)
@@ -500,9 +515,11 @@ class MsTcnFn(torch.autograd.Function):
             k, cs, d, p = _conv_geom(tc)
             if cs != s or _conv_out_len(T, k, cs, d, p) != To:
                 raise ValueError('MultiScale_TemporalConv: branch %d output length differs' % j)
-            geoms.append((k, cs, d, p))
+            pkt = _pack(_w2(tc), k, x)
+            geoms.append((k, cs, d, p, pkt[1]))
             ops.conv_fwd(Opnd(h[:, sl[j]], a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), _w2(tc), _bias(tc, x),
-                         u[:, sl[j]], k, cs, d, p, stats=(st_u[0][sl[j]], st_u[1][sl[j]]) if train else None)
+                         u[:, sl[j]], k, cs, d, p, stats=(st_u[0][sl[j]], st_u[1][sl[j]]) if train else None,
+                         wpack=pkt[0])
         if _conv_out_len(T, 3, s, 1, 1) != To:
             raise ValueError('MultiScale_TemporalConv: max-pool branch output length differs')
         ops.maxpool_fwd(Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), u[:, sl[nd]], s,
@@ -518,7 +535,9 @@ class MsTcnFn(torch.autograd.Function):
                 raise ValueError('residual branch shape mismatch')
             r_raw = _empty((N, Cout, To, V), x)
             st_r = _zeros((2, Cout), x, torch.float64) if res_mod.bn.training else None
-            ops.conv_fwd(r_src, _w2(res_mod.conv), _bias(res_mod.conv, x), r_raw, rk, rs, rd, rp, stats=st_r)
+            pkr = _pack(_w2(res_mod.conv), rk, x)
+            ops.conv_fwd(r_src, _w2(res_mod.conv), _bias(res_mod.conv, x), r_raw, rk, rs, rd, rp, stats=st_r,
+                         wpack=pkr[0])
             cr = _BnCoef(Cout, x)
             _bn_forward([res_mod.bn], [_full(Cout)], cr, st_r, N * To * V, res_mod.bn.training)
             res_mode, r, sr, hr = RES_AFFINE, r_raw, cr.scale, cr.shift
@@ -532,7 +551,8 @@ class MsTcnFn(torch.autograd.Function):
         ops.tcn_epilogue_fwd(u, cu.scale, cu.shift, res_mode, r, sr, hr, relu, out)
 
         ctx.mod, ctx.res_mod, ctx.res_kind, ctx.relu, ctx.train = mod, res_mod, res_kind, relu, train
-        ctx.geoms, ctx.coefs, ctx.packed = geoms, (ch, cu, cr), (Wh, W3)
+        ctx.geoms, ctx.coefs = geoms, (ch, cu, cr)
+        ctx.packed = (Wh, W3, pkh[1], pk3[1], pkr[1] if res_kind == 'conv' else None)
         ctx.r_is_x = r_in is None
         ctx.save_for_backward(x, r_src if res_kind == 'conv' else None, h, u, r_raw, out if relu else None)
         return out
@@ -542,7 +562,7 @@ class MsTcnFn(torch.autograd.Function):
         mod, res_mod, res_kind, relu, train = ctx.mod, ctx.res_mod, ctx.res_kind, ctx.relu, ctx.train
         x, r_src, h, u, r_raw, out = ctx.saved_tensors
         ch, cu, cr = ctx.coefs
-        Wh, W3 = ctx.packed
+        Wh, W3, pkhd, pk3d, pkrd = ctx.packed
         N, Cin, T, V = x.shape
         nd, Cb, s = mod.num_dil, mod.branch_channels, mod.stride
         nb = nd + 2
@@ -567,7 +587,7 @@ class MsTcnFn(torch.autograd.Function):
         tgrads = []
         for j in range(nd):
             tc = mod.branches[j][3].conv
-            k, cs, d, p = ctx.geoms[j]
+            k, cs, d, p, pktd = ctx.geoms[j]
             dyj = dy_op(sl[j].start, sl[j].stop)
             hj = h[:, sl[j]]
             W = _w2(tc)
@@ -575,7 +595,7 @@ class MsTcnFn(torch.autograd.Function):
             db = _zeros((Cb,), x, torch.float32)
             ops.conv_wgrad(dyj, Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), dW, db, k, cs, d, p)
             ops.conv_dgrad(dyj, W, DH[:, sl[j]], k, cs, d, p, mask=Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]]),
-                           stats=(sh[0][sl[j]], sh[1][sl[j]]))
+                           stats=(sh[0][sl[j]], sh[1][sl[j]]), wpack=pktd)
             tgrads.append((dW.view_as(tc.weight), db if tc.bias is not None else None))
         ops.maxpool_bwd(dy_op(sl[nd].start, sl[nd].stop),
                         Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), DH[:, sl[nd]], s,
@@ -587,12 +607,12 @@ class MsTcnFn(torch.autograd.Function):
         dbh = _zeros((Ch,), x, torch.float32)
         ops.conv_wgrad(dh, x, dWh, dbh)
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dh, Wh, dx)
+        ops.conv_dgrad(dh, Wh, dx, wpack=pkhd)
         dy3 = dy_op(Ch, Cout)
         dW3 = _zeros(W3.shape, x, torch.float32)
         db3 = _zeros((Cb,), x, torch.float32)
         ops.conv_wgrad(dy3, x, dW3, db3, 1, s, 1, 0)
-        ops.conv_dgrad(dy3, W3, dx, 1, s, 1, 0, addend=dx)
+        ops.conv_dgrad(dy3, W3, dx, 1, s, 1, 0, addend=dx, wpack=pk3d)
 
         dr = None
         rgrads = []
@@ -606,10 +626,10 @@ class MsTcnFn(torch.autograd.Function):
             dbr = _zeros((Cout,), x, torch.float32)
             ops.conv_wgrad(dyr, r_src, dWr, dbr, rk, rs, rd, rp)
             if ctx.r_is_x:
-                ops.conv_dgrad(dyr, Wr, dx, rk, rs, rd, rp, addend=dx)
+                ops.conv_dgrad(dyr, Wr, dx, rk, rs, rd, rp, addend=dx, wpack=pkrd)
             else:
                 dr = _empty(r_src.shape, x)
-                ops.conv_dgrad(dyr, Wr, dr, rk, rs, rd, rp)
+                ops.conv_dgrad(dyr, Wr, dr, rk, rs, rd, rp, wpack=pkrd)
             rgrads = [dWr.view_as(res_mod.conv.weight), dbr if res_mod.conv.bias is not None else None, br.dgamma,
                       br.dbeta]
         elif res_kind == 'identity':
@@ -650,10 +670,11 @@ class CtgFn(torch.autograd.Function):
         Af = A.to(torch.float32).contiguous()
         W, b = _w2(mod.conv), _bias(mod.conv, x)
         y = _empty((N, KC, To, V), x)
-        ops.conv_fwd(x, W, b, y, k, s, d, p)
+        pk = _pack(W, k, x)
+        ops.conv_fwd(x, W, b, y, k, s, d, p, wpack=pk[0])
         out = _empty((N, KC // K, To, V), x)
         ops.graph_agg_fwd(y, Af, out)
-        ctx.mod, ctx.geom = mod, (k, s, d, p)
+        ctx.mod, ctx.geom, ctx.pkd = mod, (k, s, d, p), pk[1]
         ctx.save_for_backward(x, y, Af)
         ctx.a_dtype = A.dtype
         return out
@@ -672,7 +693,7 @@ class CtgFn(torch.autograd.Function):
         db = _zeros((W.shape[0],), x, torch.float32)
         ops.conv_wgrad(dy, x, dW, db, k, s, d, p)
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dy, W, dx, k, s, d, p)
+        ops.conv_dgrad(dy, W, dx, k, s, d, p, wpack=ctx.pkd)
         return dx, dA.to(ctx.a_dtype), None, dW.view_as(mod.conv.weight), (db if mod.conv.bias is not None else None)
 
 
@@ -700,7 +721,8 @@ class StGcnFn(torch.autograd.Function):
         Af = A.to(torch.float32).contiguous()
         Wg, bg = _w2(mod.gcn.conv), _bias(mod.gcn.conv, x)
         y = _empty((N, KC, Tg, V), x)
-        ops.conv_fwd(x, Wg, bg, y, gk, gs, gd, gp)
+        pkg = _pack(Wg, gk, x)
+        ops.conv_fwd(x, Wg, bg, y, gk, gs, gd, gp, wpack=pkg[0])
         agg = _empty((N, Cout, Tg, V), x)
         st_a = _zeros((2, Cout), x, torch.float64) if train else None
         ops.graph_agg_fwd(y, Af, agg, stats=st_a)
@@ -711,16 +733,20 @@ class StGcnFn(torch.autograd.Function):
         To = _conv_out_len(Tg, k, s, d, p)
         u = _empty((N, Cout, To, V), x)
         st_u = _zeros((2, Cout), x, torch.float64) if train else None
-        ops.conv_fwd(Opnd(agg, a=ca.scale, c=ca.shift, relu=True), _w2(tc), _bias(tc, x), u, k, s, d, p, stats=st_u)
+        pkt = _pack(_w2(tc), k, x)
+        ops.conv_fwd(Opnd(agg, a=ca.scale, c=ca.shift, relu=True), _w2(tc), _bias(tc, x), u, k, s, d, p, stats=st_u,
+                     wpack=pkt[0])
         cu = _BnCoef(Cout, x)
         _bn_forward([mod.tcn[3]], [_full(Cout)], cu, st_u, N * To * V, train)
         cr = r_raw = None
+        pkr = (None, None)
         if mod.res_kind == 'conv':
             rc = mod.residual[0]
             rk, rs, rd, rp = _conv_geom(rc)
             r_raw = _empty((N, Cout, To, V), x)
             st_r = _zeros((2, Cout), x, torch.float64) if train else None
-            ops.conv_fwd(x, _w2(rc), _bias(rc, x), r_raw, rk, rs, rd, rp, stats=st_r)
+            pkr = _pack(_w2(rc), rk, x)
+            ops.conv_fwd(x, _w2(rc), _bias(rc, x), r_raw, rk, rs, rd, rp, stats=st_r, wpack=pkr[0])
             cr = _BnCoef(Cout, x)
             _bn_forward([mod.residual[1]], [_full(Cout)], cr, st_r, N * To * V, train)
             res_mode, r, sr, hr = RES_AFFINE, r_raw, cr.scale, cr.shift
@@ -730,7 +756,7 @@ class StGcnFn(torch.autograd.Function):
             res_mode, r, sr, hr = RES_NONE, None, None, None
         out = _empty((N, Cout, To, V), x)
         ops.tcn_epilogue_fwd(u, cu.scale, cu.shift, res_mode, r, sr, hr, True, out)
-        ctx.mod, ctx.train, ctx.coefs = mod, train, (ca, cu, cr)
+        ctx.mod, ctx.train, ctx.coefs, ctx.pkd = mod, train, (ca, cu, cr), (pkg[1], pkt[1], pkr[1])
         ctx.save_for_backward(x, y, Af, agg, u, r_raw, out)
         ctx.a_dtype = A.dtype
         return out
@@ -757,7 +783,9 @@ class StGcnFn(torch.autograd.Function):
         ops.conv_wgrad(dyu, Opnd(agg, a=ca.scale, c=ca.shift, relu=True), dWt, dbt, k, s, d, p)
         DA = _empty(agg.shape, x)
         sa = _zeros((2, Cout), x, torch.float64)
-        ops.conv_dgrad(dyu, Wt, DA, k, s, d, p, mask=Opnd(agg, a=ca.scale, c=ca.shift), stats=(sa[0], sa[1]))
+        pkgd, pktd, pkrd = ctx.pkd
+        ops.conv_dgrad(dyu, Wt, DA, k, s, d, p, mask=Opnd(agg, a=ca.scale, c=ca.shift), stats=(sa[0], sa[1]),
+                       wpack=pktd)
         ba = _BnBwd(Cout, x)
         _bn_backward([mod.tcn[0]], [_full(Cout)], ca, ba, sa[0], sa[1], N * Tg * V, train)
         dy = _empty(y.shape, x)
@@ -771,7 +799,7 @@ class StGcnFn(torch.autograd.Function):
         dx = _empty(x.shape, x)
         rgrads = []
         if mod.res_kind == 'conv':
-            ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp)
+            ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp, wpack=pkgd)
             rc = mod.residual[0]
             rk, rs, rd, rp = _conv_geom(rc)
             br = _BnBwd(Cout, x)
@@ -781,12 +809,12 @@ class StGcnFn(torch.autograd.Function):
             dWr = _zeros(Wr.shape, x, torch.float32)
             dbr = _zeros((Cout,), x, torch.float32)
             ops.conv_wgrad(dyr, x, dWr, dbr, rk, rs, rd, rp)
-            ops.conv_dgrad(dyr, Wr, dx, rk, rs, rd, rp, addend=dx)
+            ops.conv_dgrad(dyr, Wr, dx, rk, rs, rd, rp, addend=dx, wpack=pkrd)
             rgrads = [dWr.view_as(rc.weight), dbr if rc.bias is not None else None, br.dgamma, br.dbeta]
         elif mod.res_kind == 'identity':
-            ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp, addend=G)
+            ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp, addend=G, wpack=pkgd)
         else:
-            ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp)
+            ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp, wpack=pkgd)
         grads = [dWg.view_as(mod.gcn.conv.weight), dbg if mod.gcn.conv.bias is not None else None, ba.dgamma, ba.dbeta,
                  dWt.view_as(tc.weight), dbt if tc.bias is not None else None, bu.dgamma, bu.dbeta] + rgrads
         return (dx, dA.to(ctx.a_dtype), None) + tuple(grads)

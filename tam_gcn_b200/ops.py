@@ -98,7 +98,7 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0):
+def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0, wpack=None):
     """y = conv_{k x 1}(X) (+bias); optional (sum, sumsq) fp64 statistics of y for channels >= stat_c0."""
     xp = x.p if isinstance(x, Opnd) else x
     N, Cin, T, V = xp.shape
@@ -109,12 +109,12 @@ def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0):
     ssum = ssq = None
     if stats is not None:
         ssum, ssq = _f64(stats[0], Cout - stat_c0), _f64(stats[1], Cout - stat_c0)
-    _C.check(_C.lib().tamgcn_conv_fwd(C.byref(g), _dt(xp), C.byref(xo), _f32(W, Cout * Cin * k), _f32(bias), yp, yns,
+    _C.check(_C.lib().tamgcn_conv_fwd(C.byref(g), _dt(xp), C.byref(xo), _f32(W, Cout * Cin * k), _p(wpack), _f32(bias), yp, yns,
                                       ssum, ssq, stat_c0, _stream()), 'tamgcn_conv_fwd')
 
 
 def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, bcast_scale=0.0, mask=None,
-               stats=None):
+               stats=None, wpack=None):
     """dx = conv_transpose(dY) (+addend) (+bcast*scale); optional ReLU mask + BN-backward sums."""
     dyp = dy.p if isinstance(dy, Opnd) else dy
     N, Cout, To, V = dyp.shape
@@ -135,9 +135,19 @@ def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, 
     s1 = s2 = None
     if stats is not None:
         s1, s2 = _f64(stats[0], Cin), _f64(stats[1], Cin)
-    _C.check(_C.lib().tamgcn_conv_dgrad(C.byref(g), _dt(dyp), C.byref(dyo), _f32(W, Cout * Cin * k), dxp, dxns, ap,
+    _C.check(_C.lib().tamgcn_conv_dgrad(C.byref(g), _dt(dyp), C.byref(dyo), _f32(W, Cout * Cin * k), _p(wpack), dxp, dxns, ap,
                                         ans or 0, _f32(bcast, N * Cin * V if bcast is not None else None),
                                         float(bcast_scale), mo, s1, s2, _stream()), 'tamgcn_conv_dgrad')
+
+
+def conv_pack_weights(W, Cout, Cin, k):
+    """bf16 tensor-core weight tiles for the forward and the data-gradient GEMM -> (wpack_fwd, wpack_dgrad)."""
+    l = _C.lib()
+    wf = torch.empty(l.tamgcn_conv_pack_bytes(Cout, Cin, k, 0), dtype=torch.uint8, device=W.device)
+    wd = torch.empty(l.tamgcn_conv_pack_bytes(Cout, Cin, k, 1), dtype=torch.uint8, device=W.device)
+    _C.check(l.tamgcn_conv_pack_weights(_f32(W, Cout * Cin * k), Cout, Cin, k, wf.data_ptr(), wd.data_ptr(), _stream()),
+             'tamgcn_conv_pack_weights')
+    return wf, wd
 
 
 def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):

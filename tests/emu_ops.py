@@ -52,7 +52,7 @@ def _acc(stat, v):
     stat += v.double().sum((0, 2, 3))
 
 
-def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0):
+def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0, wpack=None):
     xv = val(x)
     Cout, Cin = y.shape[1], xv.shape[1]
     out = F.conv2d(xv, W.reshape(Cout, Cin, k, 1), bias, stride=(stride, 1), padding=(pad, 0), dilation=(dil, 1))
@@ -63,7 +63,7 @@ def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0):
 
 
 def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, bcast_scale=0.0, mask=None,
-               stats=None):
+               stats=None, wpack=None):
     dyv = val(dy)
     N, Cin, T, V = dx.shape
     Cout = dyv.shape[1]
@@ -83,6 +83,10 @@ def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, 
             _acc(stats[1], g * pv)
     else:
         _store(dx, g)
+
+
+def conv_pack_weights(W, Cout, Cin, k):
+    return None, None
 
 
 def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
@@ -268,7 +272,7 @@ def graph_agg_bwd(dout, y, A, dy, dA):
         dA += torch.einsum('nkctv,nctw->kvw', y.float().reshape(N, K, KC // K, T, V), gv)
 
 
-ALL = ['conv_fwd', 'conv_dgrad', 'conv_wgrad', 'mean_t', 'ctrgc_fwd', 'ctrgc_bwd', 'bn_finalize', 'bn_bwd_coef',
+ALL = ['conv_pack_weights', 'conv_fwd', 'conv_dgrad', 'conv_wgrad', 'mean_t', 'ctrgc_fwd', 'ctrgc_bwd', 'bn_finalize', 'bn_bwd_coef',
        'gcn_epilogue_fwd', 'gcn_epilogue_bwd', 'gcn_mid_bwd', 'tcn_epilogue_fwd', 'tcn_epilogue_bwd', 'maxpool_fwd',
        'maxpool_bwd', 'graph_agg_fwd', 'graph_agg_bwd']
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(lib_built):
 
 def test_binding_covers_header(lib_built):
     from tam_gcn_b200 import _C
-    bound = set(_C.SIGNATURES) | {'tamgcn_version', 'tamgcn_last_error', 'tamgcn_launch_count'}
+    bound = set(_C.SIGNATURES) | {'tamgcn_version', 'tamgcn_last_error', 'tamgcn_launch_count', 'tamgcn_conv_pack_bytes'}
     assert bound == set(declared_symbols())
     l = _C.lib()
     assert l.tamgcn_version() >= 100
@@ -43,7 +43,7 @@ def test_argument_validation_needs_no_gpu(lib_built):
     g = _C.ConvGeom()
     g.N, g.Cin, g.Cout, g.T, g.To, g.V, g.k, g.stride, g.dil, g.pad = 1, 4, 4, 8, 7, 20, 1, 1, 1, 0   # To wrong
     op = _C.Operand()
-    rc = l.tamgcn_conv_fwd(ctypes.byref(g), 0, ctypes.byref(op), None, None, None, 0, None, None, 0, None)
+    rc = l.tamgcn_conv_fwd(ctypes.byref(g), 0, ctypes.byref(op), None, None, None, None, 0, None, None, 0, None)
     assert rc < 0 and b'inconsistent' in l.tamgcn_last_error()
     rc = l.tamgcn_ctrgc_fwd(0, None, 0, 1, 64, 8, 17, 3, 8, None, None, 0, None, None, None, None, None, 0, None, None, None)
     assert rc < 0 and b'V=17' in l.tamgcn_last_error()

@@ -68,7 +68,7 @@ def real_opnd(o):
 
 CONV_GEOMS = [  # (Cin, Cout, T, k, s, d)
     (64, 64, 12, 1, 1, 1), (3, 70, 9, 1, 1, 1), (16, 16, 13, 5, 1, 2), (16, 24, 13, 5, 2, 1), (32, 48, 12, 1, 2, 1),
-    (24, 24, 17, 9, 2, 1), (8, 8, 11, 3, 1, 4), (96, 10, 1, 1, 1, 1)]
+    (24, 24, 17, 9, 2, 1), (8, 8, 11, 3, 1, 4), (96, 10, 1, 1, 1, 1), (72, 272, 52, 1, 1, 1), (300, 40, 7, 3, 1, 1)]
 
 
 def _pad(k, d):
@@ -89,11 +89,12 @@ def test_conv_fwd(dt, geom, V, mode):
     b = rnd(g, Cout)
     c0 = Cout // 3
     outs = []
+    wp = ops.conv_pack_weights(W, Cout, Cin, k) if dt == torch.bfloat16 else (None, None)
     for fn, xo in ((ops.conv_fwd, real_opnd(x)), (E.conv_fwd, x)):
         big = torch.zeros(N, Cout + 4, To, V, device='cuda', dtype=dt)
         y = big[:, 2:2 + Cout]
         st = torch.zeros(2, Cout - c0, device='cuda', dtype=torch.float64)
-        fn(xo, W, b, y, k, s, d, p, stats=(st[0], st[1]), stat_c0=c0)
+        fn(xo, W, b, y, k, s, d, p, stats=(st[0], st[1]), stat_c0=c0, wpack=wp[0])
         outs.append((big, st))
     assert rel(outs[0][0], outs[1][0]) < tol(dt)
     assert rel(outs[0][1], outs[1][1]) < tol(dt)
@@ -114,11 +115,13 @@ def test_conv_dgrad(dt, geom, V, opts):
     bcast = rnd(g, N, Cin, 1, V) if opts == 'addend' else None
     mask = E.Opnd(rnd(g, N, Cin, T, V, dt=dt), a=coef(g, Cin, True), c=coef(g, Cin)) if opts == 'mask' else None
     outs = []
+    wp = ops.conv_pack_weights(W, Cout, Cin, k) if dt == torch.bfloat16 else (None, None)
     for fn, conv in ((ops.conv_dgrad, real_opnd), (E.conv_dgrad, lambda o: o)):
         dx = torch.zeros(N, Cin, T, V, device='cuda', dtype=dt)
         st = torch.zeros(2, Cin, device='cuda', dtype=torch.float64)
         fn(conv(dy), W, dx, k, s, d, p, addend=addend, bcast=bcast, bcast_scale=0.25,
-           mask=conv(mask) if mask is not None else None, stats=(st[0], st[1]) if mask is not None else None)
+           mask=conv(mask) if mask is not None else None, stats=(st[0], st[1]) if mask is not None else None,
+           wpack=wp[1])
         outs.append((dx, st))
     assert rel(outs[0][0], outs[1][0]) < tol(dt)
     if mask is not None:
