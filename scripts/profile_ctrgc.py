@@ -11,7 +11,9 @@ from tam_gcn_b200.ops import Opnd
 dtype = torch.bfloat16 if (len(sys.argv) < 2 or sys.argv[1] == 'bf16') else torch.float32
 N, Cout, T, V, K, R = 1024, 64, 64, 25, 3, 8
 if len(sys.argv) > 2 and sys.argv[2] == 'ucla':
-    N, Cout, T, V, K, R = 1024, 64, 52, 20, 3, 8
+    N, Cout, T, V, K, R = 2048, 64, 52, 20, 3, 8
+if len(sys.argv) > 2 and sys.argv[2] == 'ucla64':
+    N, Cout, T, V, K, R = 64, 64, 52, 20, 3, 8
 dev = 'cuda'
 g = torch.Generator(device='cuda').manual_seed(0)
 x3 = torch.randn(N, K * Cout, T, V, device=dev, generator=g).to(dtype)
@@ -26,6 +28,7 @@ gr = torch.randn(N, Cout, T, V, device=dev, generator=g).to(dtype)
 dx3 = torch.empty_like(x3)
 dx12 = torch.zeros_like(x12)
 dW4, db4, dPA, dal = torch.zeros_like(W4), torch.zeros_like(b4), torch.zeros_like(PA), torch.zeros(1, device=dev)
+fwd_only = len(sys.argv) > 3 and sys.argv[3] == 'fwd'
 for it in range(3):
     ops.ctrgc_fwd(x3, x12[:, :K * R], x12[:, K * R:], W4, b4, PA, alpha, y, stats=(st[0], st[1]))
     ops.ctrgc_bwd(Opnd(gr), x3, x12[:, :K * R], x12[:, K * R:], W4, b4, PA, alpha, dx3, dx12[:, :K * R],

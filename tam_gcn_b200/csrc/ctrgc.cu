@@ -341,6 +341,12 @@ static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, co
 
 }  // namespace tamgcn
 
+namespace tamgcn {
+int ctrgc_fwd_tc(const void* x3, long long x3ns, int N, int Cout, int T, int V, int K, int R, const float* x1,
+                 const float* x2, long long x12ns, const float* W4, const float* b4, const float* PA, const float* alpha,
+                 void* y, long long yns, double* ssum, double* ssq, cudaStream_t st);
+}
+
 using namespace tamgcn;
 
 extern "C" int tamgcn_mean_t(int dtype, const void* x, int64_t x_nstride, int N, int C, int T, int V, float* m,
@@ -376,6 +382,11 @@ extern "C" int tamgcn_ctrgc_fwd(int dtype, const void* x3, int64_t x3_nstride, i
     if (R > 16 && V == 25) g.CT = 4;
     g.x3ns = x3_nstride; g.x12ns = x12_nstride; g.yns = y_nstride;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_BF16) {     // tensor-core path (ctrgc_tc.cu); 0 = shape not covered, use the SIMT kernel
+        const int rc = ctrgc_fwd_tc(x3, x3_nstride, N, Cout, T, V, K, R, x1, x2, x12_nstride, W4, b4, PA, alpha, y, y_nstride,
+                                    stat_sum, stat_sumsq, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     if (dtype == TAMGCN_F32) return launch_fwd<float>(g, V, x3, x1, x2, W4, b4, PA, alpha, y, stat_sum, stat_sumsq, st);
     if (dtype == TAMGCN_BF16) return launch_fwd<bf16>(g, V, x3, x1, x2, W4, b4, PA, alpha, y, stat_sum, stat_sumsq, st);
     return set_error("ctrgc_fwd: bad dtype %d", dtype);

@@ -32,6 +32,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 // Bounded wait (a wedged pipeline must not hang the GPU): returns false after ~2^22 polls.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 22); ++it) {
         uint32_t done;
         asm volatile(
