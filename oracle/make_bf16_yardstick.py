@@ -27,7 +27,8 @@ for name, case in H.CASES.items():
     ks = [k for k in fx['grads'] if not k.startswith('__')]
     ga = torch.cat([p[pre + k].grad.reshape(-1) for k in ks])
     gb = torch.cat([fx['grads'][k].reshape(-1) for k in ks])
-    out[name] = dict(y=O.rel_err(y, fx['y']), dx=O.rel_err(x.grad, fx['dx']), gall=O.rel_err(ga, gb))
-    print(name, out[name])
+    gk = {k: O.rel_err(p[pre + k].grad, fx['grads'][k]) for k in ks if float(fx['grads'][k].norm()) > 0}
+    out[name] = dict(y=O.rel_err(y, fx['y']), dx=O.rel_err(x.grad, fx['dx']), gall=O.rel_err(ga, gb), g=gk)
+    print(name, {k: v for k, v in out[name].items() if k != 'g'}, 'worst g', max(gk.values()) if gk else 0)
 with open(os.path.join(ROOT, 'tests', 'golden', 'bf16_yardstick.json'), 'w') as f:
     json.dump(out, f, indent=1, sort_keys=True)

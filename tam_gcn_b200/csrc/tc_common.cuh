@@ -29,22 +29,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// Bounded wait (a wedged pipeline must not hang the GPU): returns false after ~2^22 polls.
+// Bounded wait (a wedged pipeline must not hang the GPU): returns false after ~2 s.  The suspend-time hint lets the
+// hardware park the warp until the phase completes instead of re-polling every ~100 cycles (polling warps would
+// otherwise eat a third of the issue slots of a warp-specialised CTA).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 22); ++it) {
+    for (uint32_t it = 0;; ++it) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
         if (done) return true;
+        if (it == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000LL) return false;
     }
-    return false;
 }
 
 // ---- proxies / tcgen05 fences ---------------------------------------------------------------------

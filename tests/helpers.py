@@ -89,7 +89,7 @@ def run_case(name, device='cpu', act_dtype=torch.float32):
     return dict(y=y.detach().float().cpu(), dx=x.grad.detach().float().cpu(), grads=grads, buffers=bufs)
 
 
-def compare(name, res, fx, tol_y, tol_dx, tol_g, tol_buf=None, report=None, tol_gall=None):
+def compare(name, res, fx, tol_y, tol_dx, tol_g, tol_buf=None, report=None, tol_gall=None, tol_gk=None):
     """Relative-L2 comparison against a golden fixture.  Returns the list of failures (strings)."""
     fails = []
     e_y, e_dx = O.rel_err(res['y'], fx['y']), O.rel_err(res['dx'], fx['dx'])
@@ -109,8 +109,9 @@ def compare(name, res, fx, tol_y, tol_dx, tol_g, tol_buf=None, report=None, tol_
         e = O.rel_err(res['grads'][k], gref)
         if e > worst_g:
             worst_g, worst_k = e, k
-        if not e <= tol_g:
-            fails.append('%s: grad %s rel err %.3e > %.1e' % (name, k, e, tol_g))
+        tk = max(tol_g, (tol_gk or {}).get(k, 0.0))       # per-tensor bound (bf16: cancellation-heavy tensors)
+        if not e <= tk:
+            fails.append('%s: grad %s rel err %.3e > %.1e' % (name, k, e, tk))
     if tol_gall is not None:
         ks = [k for k in fx['grads'] if k in res['grads']]
         ga = torch.cat([res['grads'][k].reshape(-1) for k in ks])

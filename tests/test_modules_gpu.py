@@ -47,14 +47,16 @@ def test_module_bf16_matches_reference(name):
     """bf16 activations: graded against the reference math under torch.autocast(bfloat16)
     (tests/golden/bf16_yardstick.json, made by oracle/make_bf16_yardstick.py): outputs, input gradient and the
     whole parameter-gradient vector no worse than 2x that yard-stick (floor 1e-2); single cancellation-heavy
-    tensors (BN weights of the max-pool branch, alpha) only bounded at 0.6 - the yard-stick itself reaches 1.0."""
+    tensors (BN weights of the max-pool branch, alpha) only bounded at max(0.6, 3x their own yard-stick error) - the
+    yard-stick itself exceeds 1.0 on them (bf16 noise larger than the true gradient)."""
     _cuda()
     ys = _yardstick()[name]
     res = H.run_case(name, 'cuda', torch.bfloat16)
     rep = []
     lim = lambda v: max(2.0 * v, 1e-2)
     fails = H.compare(name, res, H.load_fixture(name), tol_y=lim(ys['y']), tol_dx=lim(ys['dx']), tol_g=0.6,
-                      tol_buf=2e-2, report=rep, tol_gall=lim(ys['gall']))
+                      tol_buf=2e-2, report=rep, tol_gall=lim(ys['gall']),
+                      tol_gk={k: 3.0 * v for k, v in ys.get('g', {}).items()})
     print('bf16 ' + rep[0] + '  (yard-stick y %.1e dx %.1e gall %.1e)' % (ys['y'], ys['dx'], ys['gall']))
     assert not fails, '\n'.join(fails)
 
