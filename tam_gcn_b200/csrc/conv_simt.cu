@@ -337,6 +337,7 @@ int conv_dgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const void* wpack, 
                   const void* addend, long long addns, const float* bcast, float bscale, const Opnd* mask, double* s1,
                   double* s2, cudaStream_t st);
 int conv_wgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
+int conv_wgrad_tc2(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
 }
 
 extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* x, const float* W,
@@ -405,7 +406,9 @@ extern "C" int tamgcn_conv_wgrad(const tamgcn_conv_geom* g, int dtype, const tam
     const Opnd dyo = make_opnd(dy), xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        const int rc = conv_wgrad_tc(g, dyo, xo, dW, dbias, st);
+        int rc = conv_wgrad_tc2(g, dyo, xo, dW, dbias, st);        // vector-access kernel (conv_wg2.cu)
+        if (rc != 0) return rc < 0 ? rc : 0;
+        rc = conv_wgrad_tc(g, dyo, xo, dW, dbias, st);             // element-granular fallback (conv_tc.cu)
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     const int gx = cdiv((long long)p.Cin * p.k, TN), gy = cdiv(p.Cout, TM);
