@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "rows.cuh"
 #include <atomic>
+#include <cstdlib>
 
 namespace tamgcn {
 
@@ -276,6 +277,232 @@ ctrgc_bwd_kernel(CtrgcP g, Opnd go, const T* __restrict__ x3, const float* __res
     if (threadIdx.x == 0) atomicAdd(dalpha, dv[0]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, bf16 storage: the two contractions over (t) and (u) run on the tensor cores (warp-level mma.sync, fp32
+// accumulation) with every operand fragment loaded straight from global memory in its natural row layout and
+// re-distributed inside the warp with movmatrix; one warp owns one channel.  The topology tensors D, Q, dQ still live
+// in shared memory only and the parameter reductions are unchanged.  (The forward kernel, ctrgc_tc.cu, is the
+// tcgen05/TMEM one; this kernel is bound by the fp32 SIMT reductions after the two GEMMs.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// two consecutive bf16 at element offset off (4-byte access when aligned), zero when !ok / second element when !ok1
+__device__ __forceinline__ uint32_t ld_pair(const bf16* __restrict__ p, long long off, bool ok, bool ok1) {
+    if (!ok) return 0u;
+    if (ok1 && ((off & 1) == 0) && ((reinterpret_cast<uintptr_t>(p) & 3) == 0)) return __ldg(reinterpret_cast<const unsigned*>(p + off));
+    const unsigned lo = __ldg(reinterpret_cast<const unsigned short*>(p + off));
+    const unsigned hi = ok1 ? __ldg(reinterpret_cast<const unsigned short*>(p + off + 1)) : 0u;
+    return lo | (hi << 16);
+}
+__device__ __forceinline__ void st_pair(bf16* __restrict__ p, long long off, uint32_t w, bool ok, bool ok1) {
+    if (!ok) return;
+    if (ok1 && ((off & 1) == 0) && ((reinterpret_cast<uintptr_t>(p) & 3) == 0)) { *reinterpret_cast<unsigned*>(p + off) = w; return; }
+    reinterpret_cast<unsigned short*>(p)[off] = (unsigned short)(w & 0xffffu);
+    if (ok1) reinterpret_cast<unsigned short*>(p)[off + 1] = (unsigned short)(w >> 16);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256)
+ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float* __restrict__ x1,
+                     const float* __restrict__ x2, const float* __restrict__ W4, const float* __restrict__ b4,
+                     const float* __restrict__ PA, const float* __restrict__ alpha_p, bf16* __restrict__ dx3,
+                     long long dx3ns, float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha) {
+    constexpr int DP = VPad<V>::DP;
+    constexpr int NTn = (V + 7) / 8;          // 8-wide v tiles (20 -> 3, 25 -> 4)
+    constexpr int QP = 40;                    // pitch (bf16) of a Qt row: 32 u + 8 padding -> conflict-free fragment loads
+    extern __shared__ __align__(16) float smem[];
+    const int CT = g.CT, R = g.R, K = g.K, Tn = g.T;
+    float* dQs = smem;                 // [CT][V][DP]
+    float* Ds = dQs + CT * V * DP;     // [R][V][DP]
+    float* W4s = Ds + R * V * DP;      // [CT][R]
+    float* b4s = W4s + CT * R;         // [CT]
+    float* red = b4s + CT;             // [64]
+    bf16* Qt = reinterpret_cast<bf16*>(red + 64);     // [CT][8*NTn v rows][QP]   Qt[c][v][u] = Q[c][u][v]
+    const int n = blockIdx.y, c0 = blockIdx.x * CT;
+    const int nc = min(CT, g.Cout - c0);
+    const float alpha = __ldg(alpha_p);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const long long TV = (long long)Tn * V;
+
+    for (int idx = threadIdx.x; idx < CT * 8 * NTn * QP; idx += blockDim.x) Qt[idx] = __float2bfloat16_rn(0.f);
+    float dalpha_acc = 0.f;
+
+    for (int i = 0; i < K; ++i) {
+        __syncthreads();
+        build_D<V, DP>(Ds, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
+        for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
+            W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
+        for (int idx = threadIdx.x; idx < nc; idx += blockDim.x) b4s[idx] = __ldg(b4 + i * g.Cout + c0 + idx);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nc * V * V; idx += blockDim.x) {
+            const int c = idx / (V * V), rem = idx - c * V * V, u = rem / V, v = rem - u * V;
+            float acc = b4s[c];
+            const float* d = Ds + u * DP + v;
+            const float* w = W4s + c * R;
+            for (int r = 0; r < R; ++r) acc = fmaf(w[r], d[r * V * DP], acc);
+            Qt[(c * 8 * NTn + v) * QP + u] = __float2bfloat16_rn(fmaf(alpha, acc, __ldg(PA + (i * V + u) * V + v)));
+        }
+        __syncthreads();
+
+        for (int c = warp; c < nc; c += nwarp) {
+            const OpCoef cf = opnd_coef(go, c0 + c);
+            const bf16* gp = (const bf16*)go.p + (long long)n * go.pns + (long long)(c0 + c) * TV;
+            const bf16* gq = go.q ? (const bf16*)go.q + (long long)n * go.qns + (long long)(c0 + c) * TV : nullptr;
+            const bf16* xp = x3 + (long long)n * g.x3ns + ((long long)i * g.Cout + c0 + c) * TV;
+            bf16* dxp = dx3 + (long long)n * dx3ns + ((long long)i * g.Cout + c0 + c) * TV;
+            // B fragments of dx3 = g . Q  (k = u, n = v), constant over time: from Qt
+            uint32_t bq[2][NTn][2];
+            const bf16* qt = Qt + (size_t)c * 8 * NTn * QP;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NTn; ++nt) {
+                    const bf16* q0 = qt + (nt * 8 + gid) * QP + ks * 16 + 2 * tig;
+                    bq[ks][nt][0] = *reinterpret_cast<const uint32_t*>(q0);
+                    bq[ks][nt][1] = *reinterpret_cast<const uint32_t*>(q0 + 8);
+                }
+            float dq[2][NTn][4];
+#pragma unroll
+            for (int mu = 0; mu < 2; ++mu)
+#pragma unroll
+                for (int nt = 0; nt < NTn; ++nt) dq[mu][nt][0] = dq[mu][nt][1] = dq[mu][nt][2] = dq[mu][nt][3] = 0.f;
+
+            for (int t0 = 0; t0 < Tn; t0 += 16) {
+                // cotangent rows t0 + gid (+8): pairs of u = 8*b + 2*tig (+1), lazy operand applied, bf16x2
+                uint32_t ga[2][4];                       // [row half][u block]
+                uint32_t xa[2][NTn];                     // x3 rows, [row half][v block]
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = t0 + gid + 8 * h;
+                    const bool tok = t < Tn;
+                    const long long ro = (long long)t * V;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int u = 8 * b + 2 * tig;
+                        const bool ok = tok && u < V, ok1 = u + 1 < V;
+                        uint32_t w = 0u;
+                        if (ok) {
+                            const uint32_t pw = ld_pair(gp, ro + u, true, ok1);
+                            float lo = fmaf(cf.a, __uint_as_float(pw << 16), cf.c), hi = fmaf(cf.a, __uint_as_float(pw & 0xffff0000u), cf.c);
+                            if (gq) {
+                                const uint32_t qw = ld_pair(gq, ro + u, true, ok1);
+                                lo = fmaf(cf.b, __uint_as_float(qw << 16), lo);
+                                hi = fmaf(cf.b, __uint_as_float(qw & 0xffff0000u), hi);
+                            }
+                            if (go.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                            w = pack2_bf16(lo, ok1 ? hi : 0.f);
+                        }
+                        ga[h][b] = w;
+                    }
+#pragma unroll
+                    for (int b = 0; b < NTn; ++b) {
+                        const int v = 8 * b + 2 * tig;
+                        xa[h][b] = ld_pair(xp, ro + v, tok && v < V, v + 1 < V);
+                    }
+                }
+                // (a) dx3[t, v] = sum_u g[t, u] Q[u, v]
+#pragma unroll
+                for (int nt = 0; nt < NTn; ++nt) {
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t a[4] = {ga[0][2 * ks], ga[1][2 * ks], ga[0][2 * ks + 1], ga[1][2 * ks + 1]};
+                        mma_bf16_16816(d, a, bq[ks][nt][0], bq[ks][nt][1]);
+                    }
+                    const int v = 8 * nt + 2 * tig;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int t = t0 + gid + 8 * h;
+                        st_pair(dxp, (long long)t * V + v, pack2_bf16(d[2 * h], d[2 * h + 1]), t < Tn && v < V, v + 1 < V);
+                    }
+                }
+                // (b) dQ[u, v] += sum_t g[t, u] x3[t, v]: both operands re-distributed with movmatrix
+                uint32_t bx[NTn][2];
+#pragma unroll
+                for (int nt = 0; nt < NTn; ++nt) { bx[nt][0] = movm_trans(xa[0][nt]); bx[nt][1] = movm_trans(xa[1][nt]); }
+#pragma unroll
+                for (int mu = 0; mu < 2; ++mu) {
+                    const uint32_t a[4] = {movm_trans(ga[0][2 * mu]), movm_trans(ga[0][2 * mu + 1]), movm_trans(ga[1][2 * mu]),
+                                           movm_trans(ga[1][2 * mu + 1])};
+#pragma unroll
+                    for (int nt = 0; nt < NTn; ++nt) mma_bf16_16816(dq[mu][nt], a, bx[nt][0], bx[nt][1]);
+                }
+            }
+            // dQ fragments -> shared
+#pragma unroll
+            for (int mu = 0; mu < 2; ++mu)
+#pragma unroll
+                for (int nt = 0; nt < NTn; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int u = 16 * mu + gid + 8 * (e >> 1), v = 8 * nt + 2 * tig + (e & 1);
+                        if (u < V && v < V) dQs[(c * V + u) * DP + v] = dq[mu][nt][e];
+                    }
+        }
+        __syncthreads();
+
+        // dPA_i[u,v] += sum_c dQ
+        for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
+            const int u = idx / V, v = idx - u * V;
+            float s = 0.f;
+            for (int c = 0; c < nc; ++c) s += dQs[(c * V + u) * DP + v];
+            atomicAdd(dPA + (i * V + u) * V + v, s);
+        }
+        // raw[c,r] = sum_uv dQ[c,u,v] D[r,u,v] (r = R: sum_uv dQ):  dW4 += alpha raw, db4 += alpha raw[R],
+        // dalpha += sum dQ (W4.D + b4) = sum_r W4[c,r] raw[c,r] + b4[c] raw[c,R]
+        for (int task = warp; task < nc * (R + 1); task += nwarp) {
+            const int c = task / (R + 1), r = task - c * (R + 1);
+            float s = 0.f;
+            for (int idx = lane; idx < V * V; idx += 32) {
+                const int u = idx / V, v = idx - u * V;
+                const float dqv = dQs[(c * V + u) * DP + v];
+                s += (r < R) ? dqv * Ds[(r * V + u) * DP + v] : dqv;
+            }
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (r < R) {
+                    atomicAdd(dW4 + ((long long)i * g.Cout + c0 + c) * R + r, alpha * s);
+                    dalpha_acc = fmaf(W4s[c * R + r], s, dalpha_acc);
+                } else {
+                    atomicAdd(db4 + i * g.Cout + c0 + c, alpha * s);
+                    dalpha_acc = fmaf(b4s[c], s, dalpha_acc);
+                }
+            }
+        }
+        // dD[r,u,v] = alpha sum_c W4[c,r] dQ[c,u,v];  dS = dD (1 - D^2);  dx1[r,u] += sum_v dS;  dx2[r,v] -= sum_u dS
+        for (int task = threadIdx.x; task < 2 * R * V; task += blockDim.x) {
+            const int which = task / (R * V), rem = task - which * R * V, r = rem / V, w = rem - r * V;
+            float s = 0.f;
+            for (int o = 0; o < V; ++o) {
+                const int u = which ? o : w, v = which ? w : o;
+                float dd = 0.f;
+                for (int c = 0; c < nc; ++c) dd = fmaf(W4s[c * R + r], dQs[(c * V + u) * DP + v], dd);
+                const float dv = Ds[(r * V + u) * DP + v];
+                s = fmaf(dd, 1.f - dv * dv, s);
+            }
+            s *= alpha;
+            float* dst = (which ? dx2 : dx1) + (long long)n * g.x12ns + (i * R + r) * V + w;
+            atomicAdd(dst, which ? -s : s);
+        }
+    }
+    float dv[1] = {dalpha_acc};
+    block_sum<1>(dv, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha, dv[0]);
+}
+
 // raise the dynamic shared-memory limit of a kernel only when a larger size than ever before is needed
 // (warm-up calls do it; replays / CUDA-graph captures then issue no attribute call)
 template <typename K>
@@ -308,6 +535,29 @@ static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, c
     }
     count_launch();
     return check_launch("ctrgc_fwd");
+}
+
+static int launch_bwd_mma(const CtrgcP& g, int V, const Opnd& go, const void* x3, const float* x1, const float* x2,
+                          const float* W4, const float* b4, const float* PA, const float* alpha, void* dx3, long long dx3ns,
+                          float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha, cudaStream_t st) {
+    dim3 grid(cdiv(g.Cout, g.CT), g.N);
+    const int DP = V | 1, NTn = (V + 7) / 8;
+    const size_t sm = sizeof(float) * ((size_t)g.CT * V * DP + (size_t)g.R * V * DP + g.CT * g.R + g.CT + 64) +
+                      sizeof(bf16) * (size_t)g.CT * 8 * NTn * 40 + 16;
+    TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
+    if (V == 20) {
+        static std::atomic<int> cur{48 * 1024};
+        ensure_smem(ctrgc_bwd_mma_kernel<20>, cur, sm);
+        ctrgc_bwd_mma_kernel<20><<<grid, 256, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns, dx1, dx2,
+                                                        dW4, db4, dPA, dalpha);
+    } else {
+        static std::atomic<int> cur{48 * 1024};
+        ensure_smem(ctrgc_bwd_mma_kernel<25>, cur, sm);
+        ctrgc_bwd_mma_kernel<25><<<grid, 256, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns, dx1, dx2,
+                                                        dW4, db4, dPA, dalpha);
+    }
+    count_launch();
+    return check_launch("ctrgc_bwd(mma)");
 }
 
 template <typename T>
@@ -408,7 +658,11 @@ extern "C" int tamgcn_ctrgc_bwd(int dtype, const tamgcn_operand* gop, const void
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_F32)
         return launch_bwd<float>(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
-    if (dtype == TAMGCN_BF16)
+    if (dtype == TAMGCN_BF16) {
+        const char* e = getenv("TAMGCN_DISABLE_TC");
+        if (!(e && e[0] == '1'))
+            return launch_bwd_mma(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
         return launch_bwd<bf16>(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
+    }
     return set_error("ctrgc_bwd: bad dtype %d", dtype);
 }
