@@ -313,57 +313,120 @@ __device__ __forceinline__ void st_pair(bf16* __restrict__ p, long long off, uin
     if (ok1) reinterpret_cast<unsigned short*>(p)[off + 1] = (unsigned short)(w >> 16);
 }
 
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                 : "=r"(r0), "=r"(r1) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+#define CBM_CT 16            // channels per CTA (one warp each)
+#define CBM_THREADS 512
+
+// Every contraction of the backward runs on warp-level tensor-core MMAs (m16n8k16, bf16 in, fp32 accumulate):
+//   P4[c,uv]   = sum_r W4[c,r] D[r,uv]          (-> Q = alpha (P4 + b4) + PA, stored transposed as the B operand of)
+//   dx3[t,v]   = sum_u g[t,u] Q[u,v]            per channel, fragments straight from global memory
+//   dQ[u,v]    = sum_t g[t,u] x3[t,v]           per channel, operands re-distributed with movmatrix
+//   raw[c,r]   = sum_uv dQ[c,uv] D[r,uv]        (row R of D is all ones: raw[c,R] = sum_uv dQ)  -> dW4, db4, dalpha
+//   dD[r,uv]   = sum_c W4[c,r] dQ[c,uv]         -> dS = alpha dD (1 - D^2) -> dx1, dx2
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CBM_THREADS)
 ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float* __restrict__ x1,
                      const float* __restrict__ x2, const float* __restrict__ W4, const float* __restrict__ b4,
                      const float* __restrict__ PA, const float* __restrict__ alpha_p, bf16* __restrict__ dx3,
                      long long dx3ns, float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha) {
-    constexpr int DP = VPad<V>::DP;
+    constexpr int CT = CBM_CT;
+    constexpr int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8;      // uv = u*V + v; bf16 row pitch (conflict-free)
     constexpr int NTn = (V + 7) / 8;          // 8-wide v tiles (20 -> 3, 25 -> 4)
-    constexpr int QP = 40;                    // pitch (bf16) of a Qt row: 32 u + 8 padding -> conflict-free fragment loads
+    constexpr int QP = 40;                    // pitch (bf16) of a Qt row: 32 u + 8 padding
     extern __shared__ __align__(16) float smem[];
-    const int CT = g.CT, R = g.R, K = g.K, Tn = g.T;
-    float* dQs = smem;                 // [CT][V][DP]
-    float* Ds = dQs + CT * V * DP;     // [R][V][DP]
-    float* W4s = Ds + R * V * DP;      // [CT][R]
-    float* b4s = W4s + CT * R;         // [CT]
-    float* red = b4s + CT;             // [64]
-    bf16* Qt = reinterpret_cast<bf16*>(red + 64);     // [CT][8*NTn v rows][QP]   Qt[c][v][u] = Q[c][u][v]
+    const int R = g.R, K = g.K, Tn = g.T;
+    const int Rp = (R + 15) & ~15, RW = Rp + 8;          // K extent of the r contraction, pitch of W4b rows
+    const int NR = R + 1, NRt = (NR + 7) / 8, DR = NRt * 8 > Rp ? NRt * 8 : Rp;   // rows of Db (R data rows, ones row, zero rows)
+    float* Df = smem;                                   // [R][UVp]     tanh table, later dS
+    float* dQs = Df + (size_t)R * UVp;                  // [CT][UV]     fp32 dQ (for dPA)
+    float* b4s = dQs + CT * UV;                         // [CT]
+    float* x12s = b4s + CT;                             // [2][R*V]
+    float* red = x12s + 2 * R * V;                      // [64]
+    bf16* Db = reinterpret_cast<bf16*>(red + 64);       // [DR][UP]     D (bf16), ones row, zero rows
+    bf16* dQc = Db + (size_t)DR * UP;                   // [16][UP]     dQ (bf16)
+    bf16* W4b = dQc + 16 * UP;                          // [16][RW]     W4[c][r]
+    bf16* W4T = W4b + 16 * RW;                          // [Rp][24]     W4[c][r] transposed
+    bf16* Qt = W4T + Rp * 24;                           // [CT][8*NTn][QP]   Qt[c][v][u] = Q[c][u][v]
     const int n = blockIdx.y, c0 = blockIdx.x * CT;
     const int nc = min(CT, g.Cout - c0);
     const float alpha = __ldg(alpha_p);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const long long TV = (long long)Tn * V;
+    const bf16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
 
-    for (int idx = threadIdx.x; idx < CT * 8 * NTn * QP; idx += blockDim.x) Qt[idx] = __float2bfloat16_rn(0.f);
+    for (int idx = tid; idx < CT * 8 * NTn * QP; idx += CBM_THREADS) Qt[idx] = zero;
+    for (int idx = tid; idx < DR * UP; idx += CBM_THREADS) Db[idx] = (idx / UP == R && idx % UP < UV) ? one : zero;
     float dalpha_acc = 0.f;
 
     for (int i = 0; i < K; ++i) {
         __syncthreads();
-        build_D<V, DP>(Ds, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
-        for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
-            W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
-        for (int idx = threadIdx.x; idx < nc; idx += blockDim.x) b4s[idx] = __ldg(b4 + i * g.Cout + c0 + idx);
+        // ---- parameters of this subset and the tanh table ----
+        for (int idx = tid; idx < R * V; idx += CBM_THREADS) {
+            x12s[idx] = __ldg(x1 + (long long)n * g.x12ns + i * R * V + idx);
+            x12s[R * V + idx] = __ldg(x2 + (long long)n * g.x12ns + i * R * V + idx);
+        }
+        for (int idx = tid; idx < 16 * RW; idx += CBM_THREADS) {
+            const int c = idx / RW, r = idx - c * RW;
+            W4b[idx] = (c < nc && r < R) ? __float2bfloat16_rn(__ldg(W4 + ((long long)i * g.Cout + c0 + c) * R + r)) : zero;
+        }
+        for (int idx = tid; idx < Rp * 24; idx += CBM_THREADS) {
+            const int r = idx / 24, c = idx - r * 24;
+            W4T[idx] = (c < nc && r < R) ? __float2bfloat16_rn(__ldg(W4 + ((long long)i * g.Cout + c0 + c) * R + r)) : zero;
+        }
+        for (int idx = tid; idx < CT; idx += CBM_THREADS) b4s[idx] = idx < nc ? __ldg(b4 + i * g.Cout + c0 + idx) : 0.f;
+        for (int idx = tid; idx < 16 * UP; idx += CBM_THREADS) dQc[idx] = zero;
         __syncthreads();
-        for (int idx = threadIdx.x; idx < nc * V * V; idx += blockDim.x) {
-            const int c = idx / (V * V), rem = idx - c * V * V, u = rem / V, v = rem - u * V;
-            float acc = b4s[c];
-            const float* d = Ds + u * DP + v;
-            const float* w = W4s + c * R;
-            for (int r = 0; r < R; ++r) acc = fmaf(w[r], d[r * V * DP], acc);
-            Qt[(c * 8 * NTn + v) * QP + u] = __float2bfloat16_rn(fmaf(alpha, acc, __ldg(PA + (i * V + u) * V + v)));
+        for (int idx = tid; idx < R * UVp; idx += CBM_THREADS) {
+            const int r = idx / UVp, uv = idx - r * UVp;
+            float d = 0.f;
+            if (uv < UV) {
+                const int u = uv / V, v = uv - u * V;
+                d = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]);
+            }
+            Df[idx] = d;
+            Db[r * UP + uv] = __float2bfloat16_rn(d);
+        }
+        __syncthreads();
+        // ---- Q = alpha (W4 . D + b4) + PA, as Qt[c][v][u] (bf16) ----
+        for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int ks = 0; ks < Rp / 16; ++ks) {
+                const bf16* wa = W4b + gid * RW + ks * 16 + 2 * tig;
+                const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(wa), *reinterpret_cast<const uint32_t*>(wa + 8 * RW),
+                                       *reinterpret_cast<const uint32_t*>(wa + 8), *reinterpret_cast<const uint32_t*>(wa + 8 * RW + 8)};
+                uint32_t b0, b1;
+                ldsm_x2_trans(b0, b1, Db + (size_t)(ks * 16 + (lane & 15)) * UP + nt * 8);
+                mma_bf16_16816(d, a, b0, b1);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = gid + 8 * (e >> 1), uv = nt * 8 + 2 * tig + (e & 1);
+                if (c < nc && uv < UV) {
+                    const int u = uv / V, v = uv - u * V;
+                    Qt[(c * 8 * NTn + v) * QP + u] = __float2bfloat16_rn(fmaf(alpha, d[e] + b4s[c], __ldg(PA + (i * V + u) * V + v)));
+                }
+            }
         }
         __syncthreads();
 
-        for (int c = warp; c < nc; c += nwarp) {
+        // ---- per channel (one warp each): dx3 and dQ ----
+        if (warp < nc) {
+            const int c = warp;
             const OpCoef cf = opnd_coef(go, c0 + c);
             const bf16* gp = (const bf16*)go.p + (long long)n * go.pns + (long long)(c0 + c) * TV;
             const bf16* gq = go.q ? (const bf16*)go.q + (long long)n * go.qns + (long long)(c0 + c) * TV : nullptr;
             const bf16* xp = x3 + (long long)n * g.x3ns + ((long long)i * g.Cout + c0 + c) * TV;
             bf16* dxp = dx3 + (long long)n * dx3ns + ((long long)i * g.Cout + c0 + c) * TV;
-            // B fragments of dx3 = g . Q  (k = u, n = v), constant over time: from Qt
             uint32_t bq[2][NTn][2];
             const bf16* qt = Qt + (size_t)c * 8 * NTn * QP;
 #pragma unroll
@@ -381,8 +444,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                 for (int nt = 0; nt < NTn; ++nt) dq[mu][nt][0] = dq[mu][nt][1] = dq[mu][nt][2] = dq[mu][nt][3] = 0.f;
 
             for (int t0 = 0; t0 < Tn; t0 += 16) {
-                // cotangent rows t0 + gid (+8): pairs of u = 8*b + 2*tig (+1), lazy operand applied, bf16x2
-                uint32_t ga[2][4];                       // [row half][u block]
+                uint32_t ga[2][4];                       // cotangent, [row half][u block], lazy operand applied
                 uint32_t xa[2][NTn];                     // x3 rows, [row half][v block]
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -413,7 +475,6 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                         xa[h][b] = ld_pair(xp, ro + v, tok && v < V, v + 1 < V);
                     }
                 }
-                // (a) dx3[t, v] = sum_u g[t, u] Q[u, v]
 #pragma unroll
                 for (int nt = 0; nt < NTn; ++nt) {
                     float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -429,7 +490,6 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                         st_pair(dxp, (long long)t * V + v, pack2_bf16(d[2 * h], d[2 * h + 1]), t < Tn && v < V, v + 1 < V);
                     }
                 }
-                // (b) dQ[u, v] += sum_t g[t, u] x3[t, v]: both operands re-distributed with movmatrix
                 uint32_t bx[NTn][2];
 #pragma unroll
                 for (int nt = 0; nt < NTn; ++nt) { bx[nt][0] = movm_trans(xa[0][nt]); bx[nt][1] = movm_trans(xa[1][nt]); }
@@ -441,7 +501,6 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                     for (int nt = 0; nt < NTn; ++nt) mma_bf16_16816(dq[mu][nt], a, bx[nt][0], bx[nt][1]);
                 }
             }
-            // dQ fragments -> shared
 #pragma unroll
             for (int mu = 0; mu < 2; ++mu)
 #pragma unroll
@@ -449,58 +508,79 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int u = 16 * mu + gid + 8 * (e >> 1), v = 8 * nt + 2 * tig + (e & 1);
-                        if (u < V && v < V) dQs[(c * V + u) * DP + v] = dq[mu][nt][e];
+                        if (u < V && v < V) {
+                            dQs[c * UV + u * V + v] = dq[mu][nt][e];
+                            dQc[c * UP + u * V + v] = __float2bfloat16_rn(dq[mu][nt][e]);
+                        }
                     }
         }
         __syncthreads();
 
-        // dPA_i[u,v] += sum_c dQ
-        for (int idx = threadIdx.x; idx < V * V; idx += blockDim.x) {
-            const int u = idx / V, v = idx - u * V;
+        // ---- dPA_i[u,v] += sum_c dQ ----
+        for (int uv = tid; uv < UV; uv += CBM_THREADS) {
             float s = 0.f;
-            for (int c = 0; c < nc; ++c) s += dQs[(c * V + u) * DP + v];
-            atomicAdd(dPA + (i * V + u) * V + v, s);
+            for (int c = 0; c < nc; ++c) s += dQs[c * UV + uv];
+            atomicAdd(dPA + i * UV + uv, s);
         }
-        // raw[c,r] = sum_uv dQ[c,u,v] D[r,u,v] (r = R: sum_uv dQ):  dW4 += alpha raw, db4 += alpha raw[R],
-        // dalpha += sum dQ (W4.D + b4) = sum_r W4[c,r] raw[c,r] + b4[c] raw[c,R]
-        for (int task = warp; task < nc * (R + 1); task += nwarp) {
-            const int c = task / (R + 1), r = task - c * (R + 1);
-            float s = 0.f;
-            for (int idx = lane; idx < V * V; idx += 32) {
-                const int u = idx / V, v = idx - u * V;
-                const float dqv = dQs[(c * V + u) * DP + v];
-                s += (r < R) ? dqv * Ds[(r * V + u) * DP + v] : dqv;
+        // ---- raw[c,r] = sum_uv dQ[c,uv] D[r,uv]  (r = R: ones row): one warp per 8 values of r ----
+        if (warp < NRt) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int ks = 0; ks < UVp / 16; ++ks) {
+                const bf16* qa = dQc + gid * UP + ks * 16 + 2 * tig;
+                const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(qa), *reinterpret_cast<const uint32_t*>(qa + 8 * UP),
+                                       *reinterpret_cast<const uint32_t*>(qa + 8), *reinterpret_cast<const uint32_t*>(qa + 8 * UP + 8)};
+                const bf16* db = Db + (size_t)(warp * 8 + gid) * UP + ks * 16 + 2 * tig;
+                mma_bf16_16816(d, a, *reinterpret_cast<const uint32_t*>(db), *reinterpret_cast<const uint32_t*>(db + 8));
             }
-            s = warp_sum(s);
-            if (lane == 0) {
-                if (r < R) {
-                    atomicAdd(dW4 + ((long long)i * g.Cout + c0 + c) * R + r, alpha * s);
-                    dalpha_acc = fmaf(W4s[c * R + r], s, dalpha_acc);
-                } else {
-                    atomicAdd(db4 + i * g.Cout + c0 + c, alpha * s);
-                    dalpha_acc = fmaf(b4s[c], s, dalpha_acc);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = gid + 8 * (e >> 1), r = warp * 8 + 2 * tig + (e & 1);
+                if (c < nc && r < R) {
+                    atomicAdd(dW4 + ((long long)i * g.Cout + c0 + c) * R + r, alpha * d[e]);
+                    dalpha_acc = fmaf(__bfloat162float(W4b[c * RW + r]), d[e], dalpha_acc);
+                } else if (c < nc && r == R) {
+                    atomicAdd(db4 + i * g.Cout + c0 + c, alpha * d[e]);
+                    dalpha_acc = fmaf(b4s[c], d[e], dalpha_acc);
                 }
             }
         }
-        // dD[r,u,v] = alpha sum_c W4[c,r] dQ[c,u,v];  dS = dD (1 - D^2);  dx1[r,u] += sum_v dS;  dx2[r,v] -= sum_u dS
-        for (int task = threadIdx.x; task < 2 * R * V; task += blockDim.x) {
-            const int which = task / (R * V), rem = task - which * R * V, r = rem / V, w = rem - r * V;
-            float s = 0.f;
-            for (int o = 0; o < V; ++o) {
-                const int u = which ? o : w, v = which ? w : o;
-                float dd = 0.f;
-                for (int c = 0; c < nc; ++c) dd = fmaf(W4s[c * R + r], dQs[(c * V + u) * DP + v], dd);
-                const float dv = Ds[(r * V + u) * DP + v];
-                s = fmaf(dd, 1.f - dv * dv, s);
+        // ---- dD[r,uv] = sum_c W4[c,r] dQ[c,uv];  dS = alpha dD (1 - D^2) overwrites the tanh table ----
+        for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
+            uint32_t b0, b1;
+            ldsm_x2_trans(b0, b1, dQc + (size_t)(lane & 15) * UP + nt * 8);
+            for (int mt = 0; mt < Rp / 16; ++mt) {
+                const bf16* wa = W4T + (mt * 16 + gid) * 24 + 2 * tig;
+                const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(wa), *reinterpret_cast<const uint32_t*>(wa + 8 * 24),
+                                       *reinterpret_cast<const uint32_t*>(wa + 8), *reinterpret_cast<const uint32_t*>(wa + 8 * 24 + 8)};
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16_16816(d, a, b0, b1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = mt * 16 + gid + 8 * h, uv = nt * 8 + 2 * tig;
+                    if (r < R) {
+                        float2* pd = reinterpret_cast<float2*>(Df + (size_t)r * UVp + uv);
+                        const float2 dv = *pd;
+                        *pd = make_float2(alpha * d[2 * h] * (1.f - dv.x * dv.x), alpha * d[2 * h + 1] * (1.f - dv.y * dv.y));
+                    }
+                }
             }
-            s *= alpha;
+        }
+        __syncthreads();
+        // ---- dx1[r,u] += sum_v dS[r,u,v];  dx2[r,v] -= sum_u dS[r,u,v] ----
+        for (int task = tid; task < 2 * R * V; task += CBM_THREADS) {
+            const int which = task / (R * V), rem = task - which * R * V, r = rem / V, w = rem - r * V;
+            const float* ds = Df + (size_t)r * UVp + (which ? w : w * V);
+            const int step = which ? V : 1;
+            float s = 0.f;
+#pragma unroll 5
+            for (int o = 0; o < V; ++o) s += ds[o * step];
             float* dst = (which ? dx2 : dx1) + (long long)n * g.x12ns + (i * R + r) * V + w;
             atomicAdd(dst, which ? -s : s);
         }
     }
     float dv[1] = {dalpha_acc};
     block_sum<1>(dv, red);
-    if (threadIdx.x == 0) atomicAdd(dalpha, dv[0]);
+    if (tid == 0) atomicAdd(dalpha, dv[0]);
 }
 
 // raise the dynamic shared-memory limit of a kernel only when a larger size than ever before is needed
@@ -537,27 +617,36 @@ static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, c
     return check_launch("ctrgc_fwd");
 }
 
-static int launch_bwd_mma(const CtrgcP& g, int V, const Opnd& go, const void* x3, const float* x1, const float* x2,
+static size_t ctrgc_bwd_mma_smem(int V, int R) {
+    const int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8, NTn = (V + 7) / 8;
+    const int Rp = (R + 15) & ~15, RW = Rp + 8, NRt = (R + 1 + 7) / 8, DR = NRt * 8 > Rp ? NRt * 8 : Rp;
+    return sizeof(float) * ((size_t)R * UVp + (size_t)CBM_CT * UV + CBM_CT + 2 * (size_t)R * V + 64) +
+           sizeof(bf16) * ((size_t)DR * UP + 16 * (size_t)UP + 16 * RW + (size_t)Rp * 24 + (size_t)CBM_CT * 8 * NTn * 40) + 16;
+}
+
+// returns 1 if launched, 0 if the shape does not fit (caller falls back to the SIMT kernel), <0 on error
+static int launch_bwd_mma(const CtrgcP& g0, int V, const Opnd& go, const void* x3, const float* x1, const float* x2,
                           const float* W4, const float* b4, const float* PA, const float* alpha, void* dx3, long long dx3ns,
                           float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha, cudaStream_t st) {
+    CtrgcP g = g0;
+    g.CT = CBM_CT;
+    const size_t sm = ctrgc_bwd_mma_smem(V, g.R);
+    if (sm > 227 * 1024 || g.R > 128 || (g.R & 1)) return 0;
     dim3 grid(cdiv(g.Cout, g.CT), g.N);
-    const int DP = V | 1, NTn = (V + 7) / 8;
-    const size_t sm = sizeof(float) * ((size_t)g.CT * V * DP + (size_t)g.R * V * DP + g.CT * g.R + g.CT + 64) +
-                      sizeof(bf16) * (size_t)g.CT * 8 * NTn * 40 + 16;
-    TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
     if (V == 20) {
         static std::atomic<int> cur{48 * 1024};
         ensure_smem(ctrgc_bwd_mma_kernel<20>, cur, sm);
-        ctrgc_bwd_mma_kernel<20><<<grid, 256, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns, dx1, dx2,
-                                                        dW4, db4, dPA, dalpha);
+        ctrgc_bwd_mma_kernel<20><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns,
+                                                                dx1, dx2, dW4, db4, dPA, dalpha);
     } else {
         static std::atomic<int> cur{48 * 1024};
         ensure_smem(ctrgc_bwd_mma_kernel<25>, cur, sm);
-        ctrgc_bwd_mma_kernel<25><<<grid, 256, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns, dx1, dx2,
-                                                        dW4, db4, dPA, dalpha);
+        ctrgc_bwd_mma_kernel<25><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns,
+                                                                dx1, dx2, dW4, db4, dPA, dalpha);
     }
     count_launch();
-    return check_launch("ctrgc_bwd(mma)");
+    const int rc = check_launch("ctrgc_bwd(mma)");
+    return rc < 0 ? rc : 1;
 }
 
 template <typename T>
@@ -660,8 +749,10 @@ extern "C" int tamgcn_ctrgc_bwd(int dtype, const tamgcn_operand* gop, const void
         return launch_bwd<float>(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
     if (dtype == TAMGCN_BF16) {
         const char* e = getenv("TAMGCN_DISABLE_TC");
-        if (!(e && e[0] == '1'))
-            return launch_bwd_mma(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
+        if (!(e && e[0] == '1')) {
+            const int rc = launch_bwd_mma(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
+            if (rc != 0) return rc < 0 ? rc : 0;
+        }
         return launch_bwd<bf16>(g, V, go, x3, x1, x2, W4, b4, PA, alpha, dx3, dx3_nstride, dx1, dx2, dW4, db4, dPA, dalpha, st);
     }
     return set_error("ctrgc_bwd: bad dtype %d", dtype);
