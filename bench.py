@@ -173,8 +173,8 @@ class ClockSampler:
 def ctrgc_roofline(dtype, peak_gbs, peak_src):
     from tam_gcn_b200 import ops
     dev = torch.device('cuda')
-    # NTU-shaped l2-l4 block at large batch: N'=1024, Cout=64, T=64, V=25, K=3, R=8
-    N, Cout, T, V, K, R = 1024, 64, 64, 25, 3, 8
+    # the headline (NW-UCLA) l2-l4 block shape at an HBM-resident batch: N'=2048, Cout=64, T=52, V=20, K=3, R=8
+    N, Cout, T, V, K, R = 2048, 64, 52, 20, 3, 8
     s = 2 if dtype == torch.bfloat16 else 4
     g = torch.Generator(device='cuda').manual_seed(0)
     x3 = torch.randn(N, K * Cout, T, V, device=dev, generator=g).to(dtype)
@@ -191,7 +191,7 @@ def ctrgc_roofline(dtype, peak_gbs, peak_src):
     for _ in range(3):
         run()
     torch.cuda.synchronize()
-    iters = 10
+    iters = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -200,8 +200,11 @@ def ctrgc_roofline(dtype, peak_gbs, peak_src):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     ach = alg / (ms * 1e-3) / 1e9
-    return dict(bound='hbm', kernel='ctrgc_fwd_kernel', achieved=ach, peak=peak_gbs, unit='GB/s', frac=ach / peak_gbs,
-                traffic=None, peak_source=peak_src, algorithmic_bytes=alg, ms_per_launch=ms,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full (profiles/r01e_ctrgc_tc_full.txt: 827.3 MB read + 252.1 MB written)
+    traffic = 1079449088 if dtype == torch.bfloat16 else None
+    return dict(bound='hbm', kernel='ctrgc_fwd_tc_kernel (tcgen05)' if dtype == torch.bfloat16 else 'ctrgc_fwd_kernel',
+                achieved=ach, peak=peak_gbs, unit='GB/s', frac=ach / peak_gbs,
+                traffic=traffic, peak_source=peak_src, algorithmic_bytes=alg, ms_per_launch=ms,
                 shape=dict(N=N, Cout=Cout, T=T, V=V, K=K, R=R, dtype=str(dtype).replace('torch.', '')),
                 note='inputs %.2f GB > 126 MB L2; back-to-back launches' % (x3.numel() * s / 1e9))
 

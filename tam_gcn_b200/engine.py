@@ -15,12 +15,12 @@ import torch.nn.functional as F
 
 class Trainer:
     def __init__(self, model, lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-4, use_graph=True,
-                 process_group=None):
+                 process_group=None, fused=True):
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
         # the reference's optimiser (processor/recognition_rgb.py:21-28): SGD, momentum 0.9, nesterov, weight decay
         self.opt = torch.optim.SGD(self.params, lr=lr, momentum=momentum, nesterov=nesterov,
-                                   weight_decay=weight_decay, fused=True)
+                                   weight_decay=weight_decay, fused=fused)
         self.use_graph = use_graph
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.pg = process_group
