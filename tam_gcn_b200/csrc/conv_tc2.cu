@@ -29,12 +29,11 @@ struct ConvP {
 
 // 16 warps, 128 registers per thread (the epilogue needs ~120; spills are poison here: with ~220 KB of the SM's
 // 228 KB configured as shared memory there is next to no L1 left to catch them)
-#define C2_EPI_T 256          // warps 0-7: epilogue
-#define C2_PR_W0 8
-#define C2_MMA_W 8            // warp 8: MMA issue
-#define C2_PR_T0 288          // warps 9-15: producers
-#define C2_PR_T 224
-#define C2_THREADS 512
+// Warp roles are a launch-time split: warps [0, n_epi) epilogue (n_epi = 8 or 16), warp n_epi MMA issue, the rest
+// producers.  Kernels whose epilogue has no addend / mask / broadcast extras fit 80 registers and run 24 warps; the
+// others run 16 warps at 128 registers.
+#define C2_THREADS_BIG 768
+#define C2_THREADS_SMALL 512
 #define C2_SMAX 6
 #define C2_MAXU 8
 #define C2_TWAIT(acc, call) do { const long long t0_ = clock64(); call; acc += clock64() - t0_; } while (0)
@@ -59,7 +58,7 @@ struct C2P {
     ConvP g;
     int IC, OC, Lin, Lout, KT, KTp, nchunk;
     int MT_total, n_oct, NT, NTp, nblk, tps, n_tiles;
-    int gran, upr, fast, vec, S, lag, tmem_cols;
+    int gran, upr, fast, vec, S, lag, tmem_cols, n_epi;
     uint32_t x_bytes, q_bytes, stage_bytes, off_hdr, off_coef, off_stg;
     long long ons;
     int dbg;                 // TAMGCN_C2_DBG (profiling aid): 8 = print per-role blocked cycles of block 0
@@ -183,8 +182,8 @@ __device__ __forceinline__ void c2_xform_inplace(uint32_t dst, uint32_t dstq, bo
     c2_xform_store<GR>(dst, w, q, has_q, a, b, c, relu);
 }
 
-template <int MODE, int PLAIN>
-__global__ void __launch_bounds__(C2_THREADS, 1)
+template <int MODE, int PLAIN, int EXTRA>
+__global__ void __launch_bounds__(EXTRA ? C2_THREADS_SMALL : C2_THREADS_BIG, 1)
 conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restrict__ out, C2Epi ep) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -192,6 +191,8 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
     float* coef = (float*)(smem + p.off_coef);           // [3][IC]
     const ConvP g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C2_THREADS = (int)blockDim.x, C2_MMA_W = p.n_epi, C2_PR_W0 = p.n_epi, C2_EPI_T = p.n_epi * 32;
+    const int C2_PR_T0 = (p.n_epi + 1) * 32, C2_PR_T = C2_THREADS - C2_PR_T0;
     const int S = p.S, NT = p.NT, IC = p.IC, OC = p.OC, Lin = p.Lin, Lout = p.Lout;
     const int mtmax = min(2, p.MT_total);
     const int oct = blockIdx.x % p.n_oct, mt0 = oct * 2, mt_cnt = min(2, p.MT_total - mt0);
@@ -222,7 +223,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
     if (warp < C2_PR_W0) {
         // =============================== epilogue (8 warps) ===============================
         // warp -> TMEM lane quarter q (hardware rule: warp % 4); the (channel tile, 32-column block) items of a quarter
-        // are dealt round-robin to its two warps.  A thread owns one channel per channel tile: BatchNorm sums in registers.
+        // are dealt round-robin to its n_epi / 4 warps.  A thread owns one channel per channel tile: BatchNorm sums in registers.
         const int q = warp & 3, grp = warp >> 2;
         float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f}, biasr[2] = {0.f, 0.f}, mar[2] = {1.f, 1.f}, mcr[2] = {0.f, 0.f};
 #pragma unroll
@@ -230,7 +231,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
             const int oc_ = (mt0 + mt) * 128 + q * 32 + lane;
             if (mt < mt_cnt && oc_ < OC) {
                 if (MODE == 0 && ep.bias) biasr[mt] = __ldg(ep.bias + oc_);
-                if (MODE == 1 && ep.has_mask) {
+                if (EXTRA && ep.has_mask) {
                     if (ep.maska) mar[mt] = __ldg(ep.maska + oc_);
                     if (ep.maskc) mcr[mt] = __ldg(ep.maskc + oc_);
                 }
@@ -245,7 +246,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
             const int buf = it & 1;
             C2_TWAIT(tw0, c2_wait(hdr, &hdr->tfull[buf], (uint32_t)((it >> 1) & 1)));
             tc_fence_after();
-            for (int item = grp; item < mt_cnt * nb; item += 2) {
+            for (int item = grp; item < mt_cnt * nb; item += (C2_EPI_T >> 7)) {
                 const int my_mt = (item >= nb) ? 1 : 0, pb = item - my_mt * nb;
                 const int ocw = (mt0 + my_mt) * 128 + q * 32;            // first channel of this warp in this channel tile
                 const int oc = ocw + lane;
@@ -254,9 +255,9 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                 const int nvalid = min(min(32, NT - pb * 32), Lout - (pos0 + pb * 32));
                 if (nvalid <= 0) continue;
                 const long long boff = (long long)oc * Lout + pos0 + pb * 32;    // inside a sample
-                const bf16* padd = (MODE == 1 && ep.addend && ocv) ? ep.addend + (long long)n * ep.addns + boff : nullptr;
-                const bf16* pmask = (MODE == 1 && ep.has_mask && ocv) ? ep.maskp + (long long)n * ep.maskns + boff : nullptr;
-                const float* pbc = (MODE == 1 && ep.bcast && ocv) ? ep.bcast + ((long long)n * OC + oc) * g.V : nullptr;
+                const bf16* padd = (EXTRA && ep.addend && ocv) ? ep.addend + (long long)n * ep.addns + boff : nullptr;
+                const bf16* pmask = (EXTRA && ep.has_mask && ocv) ? ep.maskp + (long long)n * ep.maskns + boff : nullptr;
+                const float* pbc = (EXTRA && ep.bcast && ocv) ? ep.bcast + ((long long)n * OC + oc) * g.V : nullptr;
                 int vv = (pos0 + pb * 32) % g.V;
                 float s1acc = 0.f, s2acc = 0.f;
                 const float bias_ = my_mt ? biasr[1] : biasr[0], ma_ = my_mt ? mar[1] : mar[0], mc_ = my_mt ? mcr[1] : mcr[0];
@@ -270,7 +271,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                     tmem_ld8_nowait(tcol + i0, acc);
                     tmem_wait_ld();
                     float ad[8], mk[8];
-                    if (MODE == 1) {
+                    if (EXTRA) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) { ad[e] = 0.f; mk[e] = 0.f; }
                         if (padd) c2_ld_row8(padd + i0, ad, vec, nvalid - i0);
@@ -284,7 +285,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                         if (MODE == 0) {
                             val = rnd<bf16>(val + bias_);
                             if (in) { s1acc += val; s2acc = fmaf(val, val, s2acc); }
-                        } else {
+                        } else if (EXTRA) {
                             val += ad[e];
                             if (pbc) {
                                 if (in) val = fmaf(__ldg(pbc + vv), ep.bscale, val);
@@ -306,7 +307,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                 // ---- phase 2: the warp writes whole rows (full 32-byte sectors)
                 const long long wbase = (long long)n * p.ons + (long long)ocw * Lout + pos0 + pb * 32;
                 if (vec == 8) {
-#pragma unroll 1
+#pragma unroll
                     for (int r8 = 0; r8 < 4; ++r8) {
                         const int row = r8 * 8 + (lane >> 2), piece = lane & 3;
                         uint4 v;
@@ -616,7 +617,7 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
     p.x_bytes = (uint32_t)p.nblk * 8192u;
     p.q_bytes = (xo.q && p.gran >= 4) ? p.x_bytes : 0u;       // second tensor of a lazy operand lands next to the first
     p.stage_bytes = p.x_bytes + p.q_bytes + (uint32_t)mtmax * 16384u;
-    const uint32_t szH = (sizeof(C2Hdr) + 15) & ~15u, szC = (uint32_t)((3 * p.IC * 4 + 15) & ~15), szG = 8 * 2560;
+    const uint32_t szH = (sizeof(C2Hdr) + 15) & ~15u, szC = (uint32_t)((3 * p.IC * 4 + 15) & ~15), szG = 16 * 2560;
     const uint32_t budget = 227u * 1024u - 1024u;
     const uint32_t fixed = szH + szC + szG;
     if (fixed + 2 * p.stage_bytes > budget) return 0;
@@ -641,16 +642,25 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
     if (per < 1) per = 1;
     if (per > tiles) per = tiles;
     const int grid = (int)(per * p.n_oct);
-#define C2_LAUNCH(PL)                                                                                              \
-    do {                                                                                                           \
-        static int cur = 48 * 1024;                                                                                \
-        if ((int)sm > cur) {                                                                                       \
-            cudaFuncSetAttribute(conv_tc2_kernel<MODE, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-            cur = (int)sm;                                                                                         \
-        }                                                                                                          \
-        conv_tc2_kernel<MODE, PL><<<grid, C2_THREADS, sm, st>>>(p, xo, (const uint8_t*)wpack, (bf16*)out, ep);     \
+    const bool extra = (MODE == 1) && (ep.addend || ep.has_mask || ep.bcast);
+    // split of the non-MMA warps between epilogue and producers by their estimated instruction load
+    {
+        const int nw = (extra ? C2_THREADS_SMALL : C2_THREADS_BIG) / 32;
+        const double epi_work = 6.0 * (p.OC < 256 ? p.OC : 256), prod_work = (plain ? 1.5 : (xo.q ? 14.0 : 9.0)) * p.KT;
+        p.n_epi = 8;
+        if (nw >= 24 && epi_work > prod_work) p.n_epi = 16;
+    }
+#define C2_LAUNCH(PL, EX)                                                                                              \
+    do {                                                                                                               \
+        static int cur = 48 * 1024;                                                                                    \
+        if ((int)sm > cur) {                                                                                           \
+            cudaFuncSetAttribute(conv_tc2_kernel<MODE, PL, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+            cur = (int)sm;                                                                                             \
+        }                                                                                                              \
+        conv_tc2_kernel<MODE, PL, EX><<<grid, EX ? C2_THREADS_SMALL : C2_THREADS_BIG, sm, st>>>(p, xo, (const uint8_t*)wpack, (bf16*)out, ep); \
     } while (0)
-    if (plain) C2_LAUNCH(1); else C2_LAUNCH(0);
+    if (MODE == 0 || !extra) { if (plain) C2_LAUNCH(1, 0); else C2_LAUNCH(0, 0); }
+    else { if (plain) C2_LAUNCH(1, 1); else C2_LAUNCH(0, 1); }
 #undef C2_LAUNCH
     count_launch();
     const int rc = check_launch(MODE == 0 ? "conv_fwd(tcgen05)" : "conv_dgrad(tcgen05)");
