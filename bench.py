@@ -220,6 +220,9 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if os.environ.get('BENCH_HANG_DUMP'):          # debugging aid: dump all Python stacks and exit if the run wedges
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ['BENCH_HANG_DUMP']), exit=True)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -322,6 +325,18 @@ def main():
                     loss=final_loss, wall_s_timed_region=t_wall)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # tear-down: the captured graph holds NCCL work; release it first, and never let a wedged communicator
+        # tear-down keep the (already printed) run alive
+        sys.stdout.flush()
+        dist.barrier()
+        trainer.graph = None
+        del trainer
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Timer(15.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         dist.destroy_process_group()
 
 

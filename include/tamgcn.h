@@ -66,6 +66,10 @@ typedef struct tamgcn_conv_geom {
 int64_t tamgcn_conv_pack_bytes(int Cout, int Cin, int k, int dgrad);
 int tamgcn_conv_pack_weights(const float* W, int Cout, int Cin, int k, void* wpack_fwd, void* wpack_dgrad,
                              tamgcn_stream stream);
+/* 1 if the bf16 forward (dgrad = 0) / data-gradient (dgrad = 1) kernel of this shape reads a packed buffer, 0 if it
+ * reads the fp32 weights directly (the small-channel temporal convolutions, Cin = Cout in {16, 32, 64}, k >= 2,
+ * run on warp-level MMAs with the operand staged once per time block — csrc/tconv_mma.cu). */
+int tamgcn_conv_needs_pack(int Cin, int Cout, int k, int stride, int V, int dgrad);
 /* y[n,co,to,v] = bias[co] + sum_{ci,j} W[co,ci,j] * X(n,ci,to*s + j*dil - pad, v)   (zero padding)
  * optional epilogue: per-channel sum / sum of squares of y over (n,to,v) for channels >= stat_c0
  * (stat arrays indexed co - stat_c0, "+=").  W is (Cout,Cin,k) fp32. */

@@ -338,6 +338,10 @@ int conv_dgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const void* wpack, 
                   double* s2, cudaStream_t st);
 int conv_wgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
 int conv_wgrad_tc2(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
+// warp-level MMA kernels for the small-channel temporal convolutions, tconv_mma.cu (kind: 0 forward, 1 data gradient)
+int tconv_mma_fwd_dgrad(const tamgcn_conv_geom* g, int kind, const Opnd& in, const float* W, const float* bias, void* out,
+                        long long ons, const Opnd* mask, double* s1, double* s2, int stat_c0, cudaStream_t st);
+int tconv_mma_wgrad(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* db, cudaStream_t st);
 }
 
 extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* x, const float* W,
@@ -350,7 +354,9 @@ extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgc
     const Opnd xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        const int rc = conv_fwd_tc(g, xo, wpack, bias, y, y_nstride, stat_sum, stat_sumsq, stat_c0, st);
+        int rc = tconv_mma_fwd_dgrad(g, 0, xo, W, bias, y, y_nstride, nullptr, stat_sum, stat_sumsq, stat_c0, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+        rc = conv_fwd_tc(g, xo, wpack, bias, y, y_nstride, stat_sum, stat_sumsq, stat_c0, st);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     dim3 grid(cdiv((long long)p.To * p.V, TN), cdiv(p.Cout, TM), p.N);
@@ -380,8 +386,10 @@ extern "C" int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tam
     if (mask) mo = make_opnd(mask);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        const int rc = conv_dgrad_tc(g, dyo, wpack, dx, dx_nstride, addend, addend_nstride, bcast, bcast_scale,
-                                     mask ? &mo : nullptr, s1, s2, st);
+        int rc = (!addend && !bcast) ? tconv_mma_fwd_dgrad(g, 1, dyo, W, nullptr, dx, dx_nstride, mask ? &mo : nullptr, s1, s2, 0, st) : 0;
+        if (rc != 0) return rc < 0 ? rc : 0;
+        rc = conv_dgrad_tc(g, dyo, wpack, dx, dx_nstride, addend, addend_nstride, bcast, bcast_scale,
+                           mask ? &mo : nullptr, s1, s2, st);
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     dim3 grid(cdiv((long long)p.T * p.V, TN), cdiv(p.Cin, TM), p.N);
@@ -406,7 +414,9 @@ extern "C" int tamgcn_conv_wgrad(const tamgcn_conv_geom* g, int dtype, const tam
     const Opnd dyo = make_opnd(dy), xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        int rc = conv_wgrad_tc2(g, dyo, xo, dW, dbias, st);        // vector-access kernel (conv_wg2.cu)
+        int rc = tconv_mma_wgrad(g, dyo, xo, dW, dbias, st);       // small-channel temporal convolutions (tconv_mma.cu)
+        if (rc != 0) return rc < 0 ? rc : 0;
+        rc = conv_wgrad_tc2(g, dyo, xo, dW, dbias, st);            // vector-access kernel (conv_wg2.cu)
         if (rc != 0) return rc < 0 ? rc : 0;
         rc = conv_wgrad_tc(g, dyo, xo, dW, dbias, st);             // element-granular fallback (conv_tc.cu)
         if (rc != 0) return rc < 0 ? rc : 0;

@@ -56,13 +56,19 @@ class Trainer:
 
     # ---- one optimisation step -------------------------------------------------------------------
     def _step_body(self, x, y):
+        from . import arena
         self.opt.zero_grad(set_to_none=True)
-        out = self.model(x)
-        loss = F.cross_entropy(out, y)
-        loss.backward()
-        if self.world > 1:
-            self._allreduce_grads()
-        self.opt.step()
+        ar = arena.arena(x.device)
+        ar.begin_step()                              # every zero-initialised accumulator of the step: one memset
+        try:
+            out = self.model(x)
+            loss = F.cross_entropy(out, y)
+            loss.backward()
+            if self.world > 1:
+                self._allreduce_grads()
+            self.opt.step()
+        finally:
+            ar.end_step()
         return loss.detach()
 
     def _capture(self, x, y):

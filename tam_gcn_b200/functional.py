@@ -21,7 +21,7 @@ packing (cat/stack) of a few KB of parameters, and O(C) coefficient algebra.
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import arena, ops
 from .ops import Opnd, RES_NONE, RES_IDENTITY, RES_AFFINE
 
 
@@ -43,7 +43,34 @@ def _empty(shape, like, dtype=None):
 
 
 def _zeros(shape, like, dtype):
-    return torch.zeros(shape, device=like.device, dtype=dtype)
+    """Zero-initialised accumulator; inside an engine step it is a slice of the once-per-step cleared arena."""
+    return arena.zeros(shape, dtype, like.device)
+
+
+def _packed(mod, key, params, shape):
+    """torch.cat of `params` (flattened) viewed as `shape`, without the copy: the parameters' storage is moved, once,
+    into one flat buffer that they become views of (same Parameter objects, same names and shapes, so state_dict,
+    optimisers and load_state_dict are unaffected).  The pointers are re-checked on every call (`.to()`, `.data`
+    swaps re-trigger the move); non-leaf tensors (nn.DataParallel replicas) fall back to torch.cat."""
+    packs = mod.__dict__.setdefault('_tamgcn_packs', {})
+    ent = packs.get(key)
+    if ent is not None:
+        flat, ptrs = ent
+        if len(ptrs) == len(params) and all(p.data_ptr() == q for p, q in zip(params, ptrs)):
+            return flat.view(shape)
+    movable = all(isinstance(p, nn.Parameter) and p.is_leaf and p.is_contiguous() for p in params) \
+        and not (params[0].is_cuda and torch.cuda.is_current_stream_capturing())
+    if not movable:
+        return torch.cat([p.reshape(-1) for p in params]).view(shape)
+    with torch.no_grad():
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.data = flat[off:off + n].view(p.shape)
+            off += n
+    packs[key] = (flat, [p.data_ptr() for p in params])
+    return flat.view(shape)
 
 
 def _w2(conv):
@@ -54,11 +81,12 @@ def _w2(conv):
     return w.reshape(w.shape[0], -1)
 
 
-def _pack(W2d, k, like):
-    """Tensor-core weight tiles (wpack_fwd, wpack_dgrad) when activations are bf16; (None, None) in fp32 mode."""
+def _pack(W2d, k, like, stride=1):
+    """Tensor-core weight tiles (wpack_fwd, wpack_dgrad) when activations are bf16; (None, None) in fp32 mode
+    (and per entry for the shapes whose kernel reads the fp32 weights directly)."""
     if like.dtype != torch.bfloat16:
         return None, None
-    return ops.conv_pack_weights(W2d, W2d.shape[0], W2d.shape[1] // k, k)
+    return ops.conv_pack_weights(W2d, W2d.shape[0], W2d.shape[1] // k, k, stride, like.shape[3])
 
 
 def _bias(conv, like):
@@ -131,17 +159,23 @@ def _ctrgc_pack(convs, like, extra=None):
     K = len(convs)
     R, Cin = convs[0].conv1.weight.shape[:2]
     Cout = convs[0].conv3.weight.shape[0]
-    W12 = torch.cat([_w2(c.conv1) for c in convs] + [_w2(c.conv2) for c in convs])            # (2KR, Cin)
-    b12 = torch.cat([_bias(c.conv1, like) for c in convs] + [_bias(c.conv2, like) for c in convs])
-    w3 = [_w2(c.conv3) for c in convs]
+    for c in convs:
+        _w2(c.conv1), _w2(c.conv2), _w2(c.conv3), _w2(c.conv4)                                # dtype checks
+    own = convs[0]                                                                            # the packs hang off the first CTRGC
+    W12 = _packed(own, 'W12', [c.conv1.weight for c in convs] + [c.conv2.weight for c in convs], (2 * K * R, Cin))
+    b12 = _packed(own, 'b12', [_bias(c.conv1, like) for c in convs] + [_bias(c.conv2, like) for c in convs], (2 * K * R,))
+    w3 = [c.conv3.weight for c in convs]
     b3 = [_bias(c.conv3, like) for c in convs]
+    Cw = K * Cout
     if extra is not None:
-        w3.append(_w2(extra))
+        _w2(extra)
+        w3.append(extra.weight)
         b3.append(_bias(extra, like))
-    W3 = torch.cat(w3) if len(w3) > 1 else w3[0].contiguous()                                # (K*Cout [+Cd], Cin)
-    b3 = torch.cat(b3) if len(b3) > 1 else b3[0].contiguous()
-    W4 = torch.stack([_w2(c.conv4) for c in convs])                                           # (K, Cout, R)
-    b4 = torch.stack([_bias(c.conv4, like) for c in convs])                                   # (K, Cout)
+        Cw += extra.weight.shape[0]
+    W3 = _packed(own, 'W3', w3, (Cw, Cin))                                                    # (K*Cout [+Cd], Cin)
+    b3 = _packed(own, 'b3', b3, (Cw,))
+    W4 = _packed(own, 'W4', [c.conv4.weight for c in convs], (K, Cout, R))
+    b4 = _packed(own, 'b4', [_bias(c.conv4, like) for c in convs], (K, Cout))
     return K, R, Cin, Cout, W12, b12, W3, b3, W4, b4
 
 
@@ -420,7 +454,7 @@ class ConvBnFn(torch.autograd.Function):
         W, b = _w2(conv), _bias(conv, x)
         raw = _empty((N, Cout, To, V), x)
         stats = _zeros((2, Cout), x, torch.float64) if train else None
-        pk = _pack(W, k, x)
+        pk = _pack(W, k, x, s)
         ops.conv_fwd(x, W, b, raw, k, s, d, p, stats=stats, wpack=pk[0])
         cf = _BnCoef(Cout, x)
         _bn_forward([bn], [_full(Cout)], cf, stats, N * To * V, train)
@@ -492,8 +526,10 @@ class MsTcnFn(torch.autograd.Function):
 
         # all 1x1 branch heads that keep T in one pass over x
         heads = [mod.branches[j][0] for j in range(nd + 1)]
-        Wh = torch.cat([_w2(c) for c in heads])
-        bh = torch.cat([_bias(c, x) for c in heads])
+        for c in heads:
+            _w2(c)
+        Wh = _packed(mod, 'Wh', [c.weight for c in heads], ((nd + 1) * Cb, Cin))
+        bh = _packed(mod, 'bh', [_bias(c, x) for c in heads], ((nd + 1) * Cb,))
         h = _empty((N, Ch, T, V), x)
         st_h = _zeros((2, Ch), x, torch.float64) if train else None
         pkh = _pack(Wh, 1, x)
@@ -515,7 +551,7 @@ class MsTcnFn(torch.autograd.Function):
             k, cs, d, p = _conv_geom(tc)
             if cs != s or _conv_out_len(T, k, cs, d, p) != To:
                 raise ValueError('MultiScale_TemporalConv: branch %d output length differs' % j)
-            pkt = _pack(_w2(tc), k, x)
+            pkt = _pack(_w2(tc), k, x, cs)
             geoms.append((k, cs, d, p, pkt[1]))
             ops.conv_fwd(Opnd(h[:, sl[j]], a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), _w2(tc), _bias(tc, x),
                          u[:, sl[j]], k, cs, d, p, stats=(st_u[0][sl[j]], st_u[1][sl[j]]) if train else None,
@@ -535,7 +571,7 @@ class MsTcnFn(torch.autograd.Function):
                 raise ValueError('residual branch shape mismatch')
             r_raw = _empty((N, Cout, To, V), x)
             st_r = _zeros((2, Cout), x, torch.float64) if res_mod.bn.training else None
-            pkr = _pack(_w2(res_mod.conv), rk, x)
+            pkr = _pack(_w2(res_mod.conv), rk, x, rs)
             ops.conv_fwd(r_src, _w2(res_mod.conv), _bias(res_mod.conv, x), r_raw, rk, rs, rd, rp, stats=st_r,
                          wpack=pkr[0])
             cr = _BnCoef(Cout, x)
@@ -670,7 +706,7 @@ class CtgFn(torch.autograd.Function):
         Af = A.to(torch.float32).contiguous()
         W, b = _w2(mod.conv), _bias(mod.conv, x)
         y = _empty((N, KC, To, V), x)
-        pk = _pack(W, k, x)
+        pk = _pack(W, k, x, s)
         ops.conv_fwd(x, W, b, y, k, s, d, p, wpack=pk[0])
         out = _empty((N, KC // K, To, V), x)
         ops.graph_agg_fwd(y, Af, out)
@@ -721,7 +757,7 @@ class StGcnFn(torch.autograd.Function):
         Af = A.to(torch.float32).contiguous()
         Wg, bg = _w2(mod.gcn.conv), _bias(mod.gcn.conv, x)
         y = _empty((N, KC, Tg, V), x)
-        pkg = _pack(Wg, gk, x)
+        pkg = _pack(Wg, gk, x, gs)
         ops.conv_fwd(x, Wg, bg, y, gk, gs, gd, gp, wpack=pkg[0])
         agg = _empty((N, Cout, Tg, V), x)
         st_a = _zeros((2, Cout), x, torch.float64) if train else None
@@ -733,7 +769,7 @@ class StGcnFn(torch.autograd.Function):
         To = _conv_out_len(Tg, k, s, d, p)
         u = _empty((N, Cout, To, V), x)
         st_u = _zeros((2, Cout), x, torch.float64) if train else None
-        pkt = _pack(_w2(tc), k, x)
+        pkt = _pack(_w2(tc), k, x, s)
         ops.conv_fwd(Opnd(agg, a=ca.scale, c=ca.shift, relu=True), _w2(tc), _bias(tc, x), u, k, s, d, p, stats=st_u,
                      wpack=pkt[0])
         cu = _BnCoef(Cout, x)
@@ -745,7 +781,7 @@ class StGcnFn(torch.autograd.Function):
             rk, rs, rd, rp = _conv_geom(rc)
             r_raw = _empty((N, Cout, To, V), x)
             st_r = _zeros((2, Cout), x, torch.float64) if train else None
-            pkr = _pack(_w2(rc), rk, x)
+            pkr = _pack(_w2(rc), rk, x, rs)
             ops.conv_fwd(x, _w2(rc), _bias(rc, x), r_raw, rk, rs, rd, rp, stats=st_r, wpack=pkr[0])
             cr = _BnCoef(Cout, x)
             _bn_forward([mod.residual[1]], [_full(Cout)], cr, st_r, N * To * V, train)

@@ -140,13 +140,17 @@ def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, 
                                         float(bcast_scale), mo, s1, s2, _stream()), 'tamgcn_conv_dgrad')
 
 
-def conv_pack_weights(W, Cout, Cin, k):
-    """bf16 tensor-core weight tiles for the forward and the data-gradient GEMM -> (wpack_fwd, wpack_dgrad)."""
+def conv_pack_weights(W, Cout, Cin, k, stride=1, V=0):
+    """bf16 tensor-core weight tiles for the forward and the data-gradient GEMM -> (wpack_fwd, wpack_dgrad).
+    An entry is None when the kernel serving that shape reads the fp32 weights directly (tamgcn_conv_needs_pack)."""
     l = _C.lib()
-    wf = torch.empty(l.tamgcn_conv_pack_bytes(Cout, Cin, k, 0), dtype=torch.uint8, device=W.device)
-    wd = torch.empty(l.tamgcn_conv_pack_bytes(Cout, Cin, k, 1), dtype=torch.uint8, device=W.device)
-    _C.check(l.tamgcn_conv_pack_weights(_f32(W, Cout * Cin * k), Cout, Cin, k, wf.data_ptr(), wd.data_ptr(), _stream()),
-             'tamgcn_conv_pack_weights')
+    nf = V <= 0 or l.tamgcn_conv_needs_pack(Cin, Cout, k, stride, V, 0)
+    nd = V <= 0 or l.tamgcn_conv_needs_pack(Cin, Cout, k, stride, V, 1)
+    wf = torch.empty(l.tamgcn_conv_pack_bytes(Cout, Cin, k, 0), dtype=torch.uint8, device=W.device) if nf else None
+    wd = torch.empty(l.tamgcn_conv_pack_bytes(Cout, Cin, k, 1), dtype=torch.uint8, device=W.device) if nd else None
+    if nf or nd:
+        _C.check(l.tamgcn_conv_pack_weights(_f32(W, Cout * Cin * k), Cout, Cin, k, _p(wf), _p(wd), _stream()),
+                 'tamgcn_conv_pack_weights')
     return wf, wd
 
 
