@@ -14,6 +14,10 @@ if len(sys.argv) > 2 and sys.argv[2] == 'ucla':
     N, Cout, T, V, K, R = 2048, 64, 52, 20, 3, 8
 if len(sys.argv) > 2 and sys.argv[2] == 'ucla64':
     N, Cout, T, V, K, R = 64, 64, 52, 20, 3, 8
+if len(sys.argv) > 2 and sys.argv[2] == 'l6_64':
+    N, Cout, T, V, K, R = 64, 128, 26, 20, 3, 16
+if len(sys.argv) > 2 and sys.argv[2] == 'l9_64':
+    N, Cout, T, V, K, R = 64, 256, 13, 20, 3, 32
 dev = 'cuda'
 g = torch.Generator(device='cuda').manual_seed(0)
 x3 = torch.randn(N, K * Cout, T, V, device=dev, generator=g).to(dtype)

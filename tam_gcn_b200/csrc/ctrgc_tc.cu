@@ -312,7 +312,10 @@ ctrgc_fwd_tc_kernel(CtcP p, const bf16* __restrict__ x3, const float* __restrict
             const int TRv = min(TR, p.T - t0), CTv = min(CT, p.Cout - c0);
             const int buf = it & 1;
             uint8_t* ob = outs + (size_t)buf * (P * 128 * V * 2);
-            CTC_TWAIT(tw0, ctc_wait(hdr, &hdr->tfull[buf], (uint32_t)((it >> 1) & 1)));
+            // one warp watches the mbarrier; the others park on a hardware barrier (a parked warp issues nothing,
+            // a polling one costs issue slots the builders need)
+            if (warp == 0) CTC_TWAIT(tw0, ctc_wait(hdr, &hdr->tfull[buf], (uint32_t)((it >> 1) & 1)));
+            bar_sync(3, CTC_EPI_T);
             tc_fence_after();
             for (int sp = my_sp; sp < P; sp += 2) {
                 float acc[Cf::VN];
@@ -489,7 +492,8 @@ ctrgc_fwd_tc_kernel(CtcP p, const bf16* __restrict__ x3, const float* __restrict
             const int s = it % S, ph = (it / S) & 1;
             const uint32_t sA = s0 + (uint32_t)s * p.stage_bytes;
             const bf16* xn = x3 + (long long)n * p.x3ns;
-            CTC_TWAIT(tw0, ctc_wait(hdr, &hdr->empty[s], (uint32_t)(ph ^ 1)));
+            if (lt < 32) CTC_TWAIT(tw0, ctc_wait(hdr, &hdr->empty[s], (uint32_t)(ph ^ 1)));
+            bar_sync(4 + lg, LGT);
             for (int sp = 0; sp < P; ++sp) {
                 const int cs = c0 + sp * G, Gv = min(G, p.Cout - cs);
                 if (Gv <= 0 || (p.dbg & 1)) break;
@@ -651,8 +655,8 @@ ctrgc_fwd_tc_kernel(CtcP p, const bf16* __restrict__ x3, const float* __restrict
                 }
                 cur_n = n;
             }
+            if (qt < 32) CTC_TWAIT(tw0, ctc_wait(hdr, &hdr->empty[s], (uint32_t)(ph ^ 1)));   // one warp polls for the whole role
             CTC_TWAIT(tw1, bar_sync(2, CTC_Q_T));
-            CTC_TWAIT(tw0, ctc_wait(hdr, &hdr->empty[s], (uint32_t)(ph ^ 1)));
             const uint32_t sB = s0 + (uint32_t)s * p.stage_bytes + (uint32_t)P * p.a_bytes;
             if (!(p.dbg & 2)) {
                 const uint32_t* w4h = reinterpret_cast<const uint32_t*>(w4t);

@@ -30,23 +30,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  : "memory");
 }
 // Bounded wait (a wedged pipeline must not hang the GPU): returns false after ~2 s.  The suspend-time hint lets the
-// hardware park the warp until the phase completes instead of re-polling every ~100 cycles (polling warps would
-// otherwise eat a third of the issue slots of a warp-specialised CTA).
+// hardware park the warp for a while instead of re-polling at once, but the parking time is bounded by the
+// implementation and failed probes are common, so the retry path is kept to three instructions (probe, two
+// branches, a counter): the wall-clock watchdog is only consulted once every 2048 failed probes.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     long long t0 = 0;
 #pragma unroll 1
-    for (uint32_t it = 0;; ++it) {
+    for (uint32_t round = 0;; ++round) {
         uint32_t done;
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .pred p;\n\t.reg .pred q;\n\t.reg .u32 n;\n\t"
+            "mov.u32 n, 2048;\n\t"
+            "MBW_LOOP:\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "@p bra MBW_DONE;\n\t"
+            "sub.u32 n, n, 1;\n\t"
+            "setp.ne.u32 q, n, 0;\n\t"
+            "@q bra MBW_LOOP;\n\t"
+            "MBW_DONE:\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
         if (done) return true;
-        if (it == 0) t0 = clock64();
+        if (round == 0) t0 = clock64();
         else if (clock64() - t0 > 4000000000LL) return false;
     }
 }
