@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, 'lib', 'libtamgcn.so')
+LIB_PATH = os.environ.get('TAMGCN_LIB') or os.path.join(PKG, 'lib', 'libtamgcn.so')   # TAMGCN_LIB: A/B timing of kernel variants
 
 F32, BF16 = 0, 1
 RES_NONE, RES_IDENTITY, RES_AFFINE = 0, 1, 2

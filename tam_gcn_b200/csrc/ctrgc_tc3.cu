@@ -103,10 +103,12 @@ __device__ __forceinline__ void c3_bulk_s2g(void* dst, uint32_t src_smem, uint32
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+
+// bounded spin wait (no suspend hint); a timeout flags the CTA so that the host sees a message instead of a hang
 __device__ __forceinline__ bool c3_wait(C3Hdr* hdr, uint64_t* bar, uint32_t parity) {
-    if (hdr->error) return false;
-    if (!mbar_wait(bar, parity)) { hdr->error = 1; return false; }
-    return true;
+    if (mbar_wait_spin(bar, parity)) return true;
+    hdr->error = 1;
+    return false;
 }
 
 __global__ void __launch_bounds__(C3_THREADS, 1)
@@ -232,23 +234,36 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, C3_NMMA_N);
+            // descriptor low words of stage 0 (start address >> 4 | LBO); a stage / sub-tile / K step only adds a constant
+            const uint32_t dlo_a = ((s0 >> 4) & 0x3FFFu) | (1u << 16), dlo_b = (((s0 + 2u * C3_A_BYTES) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t dhi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            int s = 0, ph = 0;
             for (int it = 0; it < nt; ++it) {
-                const int s = it % S, ph = (it / S) & 1, buf = it & 1;
+                const int buf = it & 1;
                 c3_wait(hdr, &hdr->tempty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
                 c3_wait(hdr, &hdr->a_full[s], (uint32_t)ph);
                 c3_wait(hdr, &hdr->b_full[s], (uint32_t)ph);
                 tc_fence_after();
-                const uint32_t sA = s0 + (uint32_t)s * C3_STAGE_BYTES, sB = sA + 2u * C3_A_BYTES;
+                const uint32_t so = (uint32_t)s * (C3_STAGE_BYTES >> 4);
 #pragma unroll
                 for (int sp = 0; sp < 2; ++sp) {
                     const uint32_t td = tmem + (uint32_t)((buf * 2 + sp) * C3_NMMA_N);
-                    const uint32_t sa = sA + (uint32_t)sp * C3_A_BYTES, sb = sB + (uint32_t)sp * C3_B_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(td, umma_desc_sw128(sa + kk * 32u), umma_desc_sw128(sb + kk * 32u), idesc, kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t alo = dlo_a + so + (uint32_t)(sp * (C3_A_BYTES >> 4) + kk * 2);
+                        const uint32_t blo = dlo_b + so + (uint32_t)(sp * (C3_B_BYTES >> 4) + kk * 2);
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                            "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                            ::"r"(td), "r"(alo), "r"(blo), "r"(idesc), "r"(kk > 0 ? 1u : 0u), "r"(dhi)
+                            : "memory");
+                    }
                 }
                 umma_commit(&hdr->empty[s]);
                 umma_commit(&hdr->tfull[buf]);
+                if (++s == S) { s = 0; ph ^= 1; }
             }
         }
     } else if (tid < C3_Q_T0) {

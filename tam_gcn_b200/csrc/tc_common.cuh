@@ -33,7 +33,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 // hardware park the warp for a while instead of re-polling at once, but the parking time is bounded by the
 // implementation and failed probes are common, so the retry path is kept to three instructions (probe, two
 // branches, a counter): the wall-clock watchdog is only consulted once every 2048 failed probes.
+__device__ __forceinline__ bool mbar_wait_spin(uint64_t* bar, uint32_t parity);
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef TAMGCN_SPIN_WAIT
+    return mbar_wait_spin(bar, parity);
+#endif
     const uint32_t addr = smem_u32(bar);
     long long t0 = 0;
 #pragma unroll 1
@@ -52,6 +56,36 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (done) return true;
+        if (round == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000LL) return false;
+    }
+}
+
+// Same bounded wait without the suspend-time hint: the warp re-probes as soon as the hardware's own (short) try_wait
+// window expires.  For the single latency-critical poller of a role (the MMA issuer, the one polling warp of the
+// other roles): a hinted wait wakes up hundreds of cycles after the phase flips, and in a pipeline whose roles hand
+// tiles to each other every ~2000 cycles that wake-up latency sits on the critical path of every hand-off.
+__device__ __forceinline__ bool mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+#pragma unroll 1
+    for (uint32_t round = 0;; ++round) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .pred q;\n\t.reg .u32 n;\n\t"
+            "mov.u32 n, 4096;\n\t"
+            "MBS_LOOP:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "@p bra MBS_DONE;\n\t"
+            "sub.u32 n, n, 1;\n\t"
+            "setp.ne.u32 q, n, 0;\n\t"
+            "@q bra MBS_LOOP;\n\t"
+            "MBS_DONE:\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
             : "memory");
         if (done) return true;
         if (round == 0) t0 = clock64();
