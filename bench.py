@@ -200,9 +200,10 @@ def ctrgc_roofline(dtype, peak_gbs, peak_src):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     ach = alg / (ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full (profiles/r01e_ctrgc_tc_full.txt: 827.3 MB read + 252.1 MB written)
-    traffic = 1079449088 if dtype == torch.bfloat16 else None
-    return dict(bound='hbm', kernel='ctrgc_fwd_tc_kernel (tcgen05)' if dtype == torch.bfloat16 else 'ctrgc_fwd_kernel',
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full
+    # (profiles/r01o_ctrgc_tc3_full.txt: 826.36 MB read + 251.89 MB written)
+    traffic = 1078249216 if dtype == torch.bfloat16 else None
+    return dict(bound='hbm', kernel='ctrgc_fwd_tc3_kernel (tcgen05 + mma.sync)' if dtype == torch.bfloat16 else 'ctrgc_fwd_kernel',
                 achieved=ach, peak=peak_gbs, unit='GB/s', frac=ach / peak_gbs,
                 traffic=traffic, peak_source=peak_src, algorithmic_bytes=alg, ms_per_launch=ms,
                 shape=dict(N=N, Cout=Cout, T=T, V=V, K=K, R=R, dtype=str(dtype).replace('torch.', '')),

@@ -275,6 +275,7 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
         int soff[C3_MAXU];
         uint32_t doff[C3_MAXU];
         const unsigned nuf = (unsigned)T * 5u, totf = (unsigned)(2 * K) * nuf;
+        const int kfull = (int)(totf / C3_LD_T);
 #pragma unroll
         for (int k = 0; k < C3_MAXU; ++k) {
             const unsigned idx = lt + k * C3_LD_T;
@@ -294,13 +295,28 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
             const bf16* xn = x3 + (long long)n * p.x3ns;
             if (lt < 32) c3_wait(hdr, &hdr->empty[s], (uint32_t)(ph ^ 1));
             c3_bar_sync(4, C3_LD_T);
+            // units k < kfull exist for every thread of the role: issued without a predicate (a predicated cp.async costs
+            // a compare and two descriptor moves on top of its address arithmetic)
+            if (kfull >= 12) {
 #pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-                const uint32_t sa = sA + (uint32_t)sp * C3_A_BYTES;
-                const bf16* base = xn + (long long)(c0 + sp * 2) * T * 20;
+                for (int sp = 0; sp < 2; ++sp) {
+                    const uint32_t sa = sA + (uint32_t)sp * C3_A_BYTES;
+                    const bf16* base = xn + (long long)(c0 + sp * 2) * T * 20;
 #pragma unroll
-                for (int k = 0; k < C3_MAXU; ++k)
-                    if (soff[k] >= 0) c3_cp_async8(sa + doff[k], base + soff[k]);
+                    for (int k = 0; k < 12; ++k) c3_cp_async8(sa + doff[k], base + soff[k]);
+#pragma unroll
+                    for (int k = 12; k < C3_MAXU; ++k)
+                        if (soff[k] >= 0) c3_cp_async8(sa + doff[k], base + soff[k]);
+                }
+            } else {
+#pragma unroll
+                for (int sp = 0; sp < 2; ++sp) {
+                    const uint32_t sa = sA + (uint32_t)sp * C3_A_BYTES;
+                    const bf16* base = xn + (long long)(c0 + sp * 2) * T * 20;
+#pragma unroll
+                    for (int k = 0; k < C3_MAXU; ++k)
+                        if (soff[k] >= 0) c3_cp_async8(sa + doff[k], base + soff[k]);
+                }
             }
             c3_cp_commit();
             if (it >= lag) {
