@@ -316,7 +316,15 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     p.bq_bytes = x.q ? p.b_bytes : 0u;
     p.stage_bytes = p.a_bytes + p.aq_bytes + p.b_bytes + p.bq_bytes;
     const uint32_t szH = (sizeof(W2Hdr) + 15) & ~15u, szC = (uint32_t)(3 * (128 + NT) * 4 + 15) & ~15u;
-    const uint32_t budget = 227u * 1024u - 1024u;
+    // TAMGCN_W2_OCC=2 (experiment, off by default): two CTAs per SM with half the shared memory each.  Measured on the
+    // N-UCLA step: no gain (11.78 vs 11.52 ms) — the extra split-K atomics and prologues cost what the overlap wins.
+    static const int occ_env = [] { const char* e = getenv("TAMGCN_W2_OCC"); return e ? atoi(e) : 1; }();
+    uint32_t budget = 227u * 1024u - 1024u;
+    int occ = 1;
+    if (occ_env >= 2 && p.tmem_cols <= 256 && szH + szC + 3 * p.stage_bytes + 1024u <= 113u * 1024u) {
+        occ = 2;
+        budget = 113u * 1024u - 1024u;
+    }
     if (szH + szC + 2 * p.stage_bytes > budget) return 0;
     p.S = (int)((budget - szH - szC) / p.stage_bytes);
     if (p.S > W2_SMAX) p.S = W2_SMAX;
@@ -325,7 +333,7 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     p.off_coef = p.off_hdr + szH;
     const size_t sm = (size_t)p.off_coef + szC + 1024;
     const int gx = (g.Cout + 127) / 128, gy = (g.Cin + NT - 1) / NT;
-    long long Z = w2_num_sms() / (gx * gy);
+    long long Z = (long long)occ * w2_num_sms() / (gx * gy);
     if (Z < 1) Z = 1;
     if (Z > units) Z = units;
     if (Z > 65535) Z = 65535;
