@@ -386,20 +386,38 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
         for (int idx = tid; idx < CT; idx += CBM_THREADS) b4s[idx] = idx < nc ? __ldg(b4 + i * g.Cout + c0 + idx) : 0.f;
         for (int idx = tid; idx < 16 * UP; idx += CBM_THREADS) dQc[idx] = zero;
         __syncthreads();
-        for (int idx = tid; idx < R * UVp; idx += CBM_THREADS) {
-            const int r = idx / UVp, uv = idx - r * UVp;
-            float d = 0.f;
-            if (uv < UV) {
-                const int u = uv / V, v = uv - u * V;
-                d = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]);
+        if (V % 4 == 0) {
+            // four consecutive v of one (r, u) per step: one x1 value, one 16-byte x2 load, vector stores
+            constexpr int QR = UVp / 4, QU = V / 4;
+            for (int idx = tid; idx < R * QR; idx += CBM_THREADS) {
+                const int r = idx / QR, q = idx - r * QR, u = q / QU, v = 4 * (q - u * QU);
+                const float a = x12s[r * V + u];
+                const float4 b = *reinterpret_cast<const float4*>(x12s + R * V + r * V + v);
+                const float4 d = make_float4(tanh_fast(a - b.x), tanh_fast(a - b.y), tanh_fast(a - b.z), tanh_fast(a - b.w));
+                *reinterpret_cast<float4*>(Df + (size_t)r * UVp + 4 * q) = d;
+                *reinterpret_cast<uint2*>(Db + (size_t)r * UP + 4 * q) = make_uint2(pack2_bf16(d.x, d.y), pack2_bf16(d.z, d.w));
             }
-            Df[idx] = d;
-            Db[r * UP + uv] = __float2bfloat16_rn(d);
+        } else {
+            for (int idx = tid; idx < R * UVp; idx += CBM_THREADS) {
+                const int r = idx / UVp, uv = idx - r * UVp;
+                float d = 0.f;
+                if (uv < UV) {
+                    const int u = uv / V, v = uv - u * V;
+                    d = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]);
+                }
+                Df[idx] = d;
+                Db[r * UP + uv] = __float2bfloat16_rn(d);
+            }
         }
         __syncthreads();
         // ---- Q = alpha (W4 . D + b4) + PA, as Qt[c][v][u] (bf16) ----
         for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
             float d[4] = {0.f, 0.f, 0.f, 0.f};
+            // PA[i][uv], PA[i][uv+1] of this lane's accumulator columns: requested before the MMAs so that the global
+            // load latency is hidden behind them (it used to stall the scatter below: 10 % of the kernel's samples)
+            const int uv0 = nt * 8 + 2 * tig;
+            const float pa0 = uv0 < UV ? __ldg(PA + i * UV + uv0) : 0.f;
+            const float pa1 = uv0 + 1 < UV ? __ldg(PA + i * UV + uv0 + 1) : 0.f;
             for (int ks = 0; ks < Rp / 16; ++ks) {
                 const bf16* wa = W4b + gid * RW + ks * 16 + 2 * tig;
                 const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(wa), *reinterpret_cast<const uint32_t*>(wa + 8 * RW),
@@ -413,7 +431,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                 const int c = gid + 8 * (e >> 1), uv = nt * 8 + 2 * tig + (e & 1);
                 if (c < nc && uv < UV) {
                     const int u = uv / V, v = uv - u * V;
-                    Qt[(c * 8 * NTn + v) * QP + u] = __float2bfloat16_rn(fmaf(alpha, d[e] + b4s[c], __ldg(PA + (i * V + u) * V + v)));
+                    Qt[(c * 8 * NTn + v) * QP + u] = __float2bfloat16_rn(fmaf(alpha, d[e] + b4s[c], (e & 1) ? pa1 : pa0));
                 }
             }
         }
@@ -443,9 +461,44 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
 #pragma unroll
                 for (int nt = 0; nt < NTn; ++nt) dq[mu][nt][0] = dq[mu][nt][1] = dq[mu][nt][2] = dq[mu][nt][3] = 0.f;
 
+            const bool fastld = (V % 2 == 0) && ((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(xp) |
+                                                  (gq ? reinterpret_cast<uintptr_t>(gq) : 0)) & 3) == 0;
             for (int t0 = 0; t0 < Tn; t0 += 16) {
                 uint32_t ga[2][4];                       // cotangent, [row half][u block], lazy operand applied
                 uint32_t xa[2][NTn];                     // x3 rows, [row half][v block]
+                if (fastld) {
+                    // even V, 4-byte aligned rows: every fragment word is one aligned 32-bit load.  All loads of the time
+                    // block are issued before the first use (the element-wise path below serialises load -> use).
+                    uint32_t pw[2][4], qw[2][4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int t = t0 + gid + 8 * h;
+                        const bool tok = t < Tn;
+                        const long long ro = (long long)t * V + 2 * tig;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const bool ok = tok && 8 * b + 2 * tig < V;
+                            pw[h][b] = ok ? __ldg(reinterpret_cast<const unsigned*>(gp + ro + 8 * b)) : 0u;
+                            qw[h][b] = (ok && gq) ? __ldg(reinterpret_cast<const unsigned*>(gq + ro + 8 * b)) : 0u;
+                        }
+#pragma unroll
+                        for (int b = 0; b < NTn; ++b)
+                            xa[h][b] = (tok && 8 * b + 2 * tig < V) ? __ldg(reinterpret_cast<const unsigned*>(xp + ro + 8 * b)) : 0u;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const bool ok = (t0 + gid + 8 * h < Tn) && 8 * b + 2 * tig < V;
+                            float lo = fmaf(cf.a, __uint_as_float(pw[h][b] << 16), cf.c), hi = fmaf(cf.a, __uint_as_float(pw[h][b] & 0xffff0000u), cf.c);
+                            if (gq) {
+                                lo = fmaf(cf.b, __uint_as_float(qw[h][b] << 16), lo);
+                                hi = fmaf(cf.b, __uint_as_float(qw[h][b] & 0xffff0000u), hi);
+                            }
+                            if (go.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                            ga[h][b] = ok ? pack2_bf16(lo, hi) : 0u;
+                        }
+                } else {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int t = t0 + gid + 8 * h;
@@ -474,6 +527,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                         const int v = 8 * b + 2 * tig;
                         xa[h][b] = ld_pair(xp, ro + v, tok && v < V, v + 1 < V);
                     }
+                }
                 }
 #pragma unroll
                 for (int nt = 0; nt < NTn; ++nt) {
