@@ -365,7 +365,10 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
     const bf16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
 
     for (int idx = tid; idx < CT * 8 * NTn * QP; idx += CBM_THREADS) Qt[idx] = zero;
-    for (int idx = tid; idx < DR * UP; idx += CBM_THREADS) Db[idx] = (idx / UP == R && idx % UP < UV) ? one : zero;
+    // Db: zero everywhere (16-byte stores; DR * UP * 2 bytes is a multiple of 16), then the ones row
+    for (int idx = tid; idx < DR * UP / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Db)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    for (int idx = tid; idx < UV; idx += CBM_THREADS) Db[R * UP + idx] = one;
     float dalpha_acc = 0.f;
 
     for (int i = 0; i < K; ++i) {
@@ -621,15 +624,40 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
         }
         __syncthreads();
         // ---- dx1[r,u] += sum_v dS[r,u,v];  dx2[r,v] -= sum_u dS[r,u,v] ----
-        for (int task = tid; task < 2 * R * V; task += CBM_THREADS) {
-            const int which = task / (R * V), rem = task - which * R * V, r = rem / V, w = rem - r * V;
-            const float* ds = Df + (size_t)r * UVp + (which ? w : w * V);
-            const int step = which ? V : 1;
-            float s = 0.f;
+        if (V % 4 == 0) {
+            // 16-byte shared-memory loads: a dx1 task sums one row of V values, a dx2 task four adjacent columns
+            constexpr int QU = V / 4;
+            for (int task = tid; task < R * V; task += CBM_THREADS) {
+                const int r = task / V, u = task - r * V;
+                const float4* ds = reinterpret_cast<const float4*>(Df + (size_t)r * UVp + u * V);
+                float s = 0.f;
+#pragma unroll
+                for (int o = 0; o < QU; ++o) { const float4 d = ds[o]; s += (d.x + d.y) + (d.z + d.w); }
+                atomicAdd(dx1 + (long long)n * g.x12ns + (i * R + r) * V + u, s);
+            }
+            for (int task = tid; task < R * QU; task += CBM_THREADS) {
+                const int r = task / QU, vq = task - r * QU;
+                const float* ds = Df + (size_t)r * UVp + 4 * vq;
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 5
-            for (int o = 0; o < V; ++o) s += ds[o * step];
-            float* dst = (which ? dx2 : dx1) + (long long)n * g.x12ns + (i * R + r) * V + w;
-            atomicAdd(dst, which ? -s : s);
+                for (int o = 0; o < V; ++o) {
+                    const float4 d = *reinterpret_cast<const float4*>(ds + o * V);
+                    s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+                }
+                float* dst = dx2 + (long long)n * g.x12ns + (i * R + r) * V + 4 * vq;
+                atomicAdd(dst, -s.x); atomicAdd(dst + 1, -s.y); atomicAdd(dst + 2, -s.z); atomicAdd(dst + 3, -s.w);
+            }
+        } else {
+            for (int task = tid; task < 2 * R * V; task += CBM_THREADS) {
+                const int which = task / (R * V), rem = task - which * R * V, r = rem / V, w = rem - r * V;
+                const float* ds = Df + (size_t)r * UVp + (which ? w : w * V);
+                const int step = which ? V : 1;
+                float s = 0.f;
+#pragma unroll 5
+                for (int o = 0; o < V; ++o) s += ds[o * step];
+                float* dst = (which ? dx2 : dx1) + (long long)n * g.x12ns + (i * R + r) * V + w;
+                atomicAdd(dst, which ? -s : s);
+            }
         }
     }
     float dv[1] = {dalpha_acc};
