@@ -8,6 +8,8 @@
 // reference: models/ctrgcn.py:255-261 (unit_gcn tail), :113-119 (max-pool branch), :145-146 (cat + res),
 //            :283 (TCN_GCN_unit tail); models/stgcn.py:98-99 (st_gcn tail).
 #include "common.cuh"
+#include <cstdlib>
+#include <initializer_list>
 
 namespace tamgcn {
 
@@ -156,6 +158,209 @@ tcn_epilogue_bwd_kernel(int N, int C, int TV, const T* __restrict__ g, const T* 
     flush_stats<3>(acc, dst, c);
 }
 
+// ------------------------------------------------------------------------------------------------
+// bf16 vector variants of the five streaming kernels above: VEC (8 or 4) elements per 16- / 8-byte access, the
+// samples of a CTA walked as one flat index space (a (T*V)/VEC-vector plane is smaller than the CTA at the late
+// layers).  Same arithmetic and rounding points as the element-wise kernels; tanh is the hardware approximation
+// (2^-11 relative, below the bf16 rounding of the stored result).  Selected by the host when every pointer and
+// stride allows the vector width.
+// ------------------------------------------------------------------------------------------------
+template <int VEC> struct BVec { uint32_t w[VEC / 2]; };
+template <int VEC> __device__ __forceinline__ BVec<VEC> bv_ld(const bf16* p) {
+    BVec<VEC> r;
+    if (VEC == 8) { const uint4 u = __ldg(reinterpret_cast<const uint4*>(p)); r.w[0] = u.x; r.w[1] = u.y; r.w[VEC / 2 - 2] = u.z; r.w[VEC / 2 - 1] = u.w; }
+    else { const uint2 u = __ldg(reinterpret_cast<const uint2*>(p)); r.w[0] = u.x; r.w[1] = u.y; }
+    return r;
+}
+template <int VEC> __device__ __forceinline__ void bv_st(bf16* p, const BVec<VEC>& r) {
+    if (VEC == 8) *reinterpret_cast<uint4*>(p) = make_uint4(r.w[0], r.w[1], r.w[VEC / 2 - 2], r.w[VEC / 2 - 1]);
+    else *reinterpret_cast<uint2*>(p) = make_uint2(r.w[0], r.w[1]);
+}
+__device__ __forceinline__ float bv_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bv_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t bv_pack(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ float tanh_hw(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// flat walk over the (sample, vector) pairs of CTA (c, blockIdx.y): sample n = blockIdx.y + k * gridDim.y, vector e
+#define BV_WALK_BEGIN(N_, TVv_)                                                                   \
+    const int nmine_ = ((N_) - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;          \
+    int k_ = 0, e_ = threadIdx.x;                                                                 \
+    while (e_ >= (TVv_)) { e_ -= (TVv_); ++k_; }                                                  \
+    while (k_ < nmine_) {                                                                         \
+        const int n = blockIdx.y + k_ * gridDim.y;                                                \
+        const int e = e_;
+#define BV_WALK_END(TVv_)                                                                         \
+        e_ += blockDim.x;                                                                         \
+        while (e_ >= (TVv_)) { e_ -= (TVv_); ++k_; }                                              \
+    }
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gcn_epilogue_fwd_vec_kernel(int N, int C, int TV, const bf16* __restrict__ y0, const float* __restrict__ sg,
+                            const float* __restrict__ hg, const bf16* __restrict__ z, const float* __restrict__ so,
+                            const float* __restrict__ ho, int res_mode, const bf16* __restrict__ r, long long rns,
+                            const float* __restrict__ sr, const float* __restrict__ hr, bf16* __restrict__ out) {
+    const int c = blockIdx.x, TVv = TV / VEC;
+    const float a_g = sg[c], b_g = hg[c], a_o = so[c], b_o = ho[c];
+    const float a_r = (res_mode == TAMGCN_RES_AFFINE) ? sr[c] : 1.f;
+    const float b_r = (res_mode == TAMGCN_RES_AFFINE) ? hr[c] : 0.f;
+    BV_WALK_BEGIN(N, TVv)
+        const long long off = ((long long)n * C + c) * TV + (long long)e * VEC;
+        const BVec<VEC> vy = bv_ld<VEC>(y0 + off), vz = bv_ld<VEC>(z + off);
+        BVec<VEC> vr, vo;
+        if (res_mode != TAMGCN_RES_NONE) vr = bv_ld<VEC>(r + (long long)n * rns + (long long)c * TV + (long long)e * VEC);
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) {
+            float lo = fmaf(a_g, bv_lo(vy.w[j]), b_g) + tanh_hw(fmaf(a_o, bv_lo(vz.w[j]), b_o));
+            float hi = fmaf(a_g, bv_hi(vy.w[j]), b_g) + tanh_hw(fmaf(a_o, bv_hi(vz.w[j]), b_o));
+            if (res_mode != TAMGCN_RES_NONE) { lo += fmaf(a_r, bv_lo(vr.w[j]), b_r); hi += fmaf(a_r, bv_hi(vr.w[j]), b_r); }
+            vo.w[j] = bv_pack(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+        }
+        bv_st<VEC>(out + off, vo);
+    BV_WALK_END(TVv)
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gcn_epilogue_bwd_vec_kernel(int N, int C, int TV, const bf16* __restrict__ g, const bf16* __restrict__ out,
+                            const bf16* __restrict__ z, const float* __restrict__ so, const float* __restrict__ ho,
+                            bf16* __restrict__ G, bf16* __restrict__ DZ, double* s1o, double* s2o) {
+    const int c = blockIdx.x, TVv = TV / VEC;
+    const float a_o = so[c], b_o = ho[c];
+    float acc[2] = {0.f, 0.f};
+    BV_WALK_BEGIN(N, TVv)
+        const long long off = ((long long)n * C + c) * TV + (long long)e * VEC;
+        const BVec<VEC> vg = bv_ld<VEC>(g + off), vout = bv_ld<VEC>(out + off), vz = bv_ld<VEC>(z + off);
+        BVec<VEC> oG, oD;
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) {
+            const float g0 = bv_lo(vout.w[j]) > 0.f ? bv_lo(vg.w[j]) : 0.f, g1 = bv_hi(vout.w[j]) > 0.f ? bv_hi(vg.w[j]) : 0.f;
+            const float z0 = bv_lo(vz.w[j]), z1 = bv_hi(vz.w[j]);
+            const float o0 = tanh_hw(fmaf(a_o, z0, b_o)), o1 = tanh_hw(fmaf(a_o, z1, b_o));
+            oG.w[j] = bv_pack(g0, g1);
+            oD.w[j] = bv_pack(g0 * (1.f - o0 * o0), g1 * (1.f - o1 * o1));
+            const float d0 = bv_lo(oD.w[j]), d1 = bv_hi(oD.w[j]);       // the rounded values, as stored
+            acc[0] += d0 + d1;
+            acc[1] = fmaf(d0, z0, fmaf(d1, z1, acc[1]));
+        }
+        bv_st<VEC>(G + off, oG);
+        bv_st<VEC>(DZ + off, oD);
+    BV_WALK_END(TVv)
+    double* const dst[2] = {s1o, s2o};
+    flush_stats<2>(acc, dst, c);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gcn_mid_bwd_vec_kernel(int N, int C, int TV, bf16* __restrict__ G, const bf16* __restrict__ DD, bf16* __restrict__ dr,
+                       long long drns, const bf16* __restrict__ y0, const bf16* __restrict__ r, long long rns, double* s1g,
+                       double* s2g, double* s1d, double* s2d) {
+    const int c = blockIdx.x, TVv = TV / VEC;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    BV_WALK_BEGIN(N, TVv)
+        const long long off = ((long long)n * C + c) * TV + (long long)e * VEC;
+        const BVec<VEC> vg = bv_ld<VEC>(G + off), vd = bv_ld<VEC>(DD + off), vy = bv_ld<VEC>(y0 + off);
+        BVec<VEC> vr, oY, oR;
+        if (r) vr = bv_ld<VEC>(r + (long long)n * rns + (long long)c * TV + (long long)e * VEC);
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) {
+            const float g0 = bv_lo(vg.w[j]), g1 = bv_hi(vg.w[j]), d0 = bv_lo(vd.w[j]), d1 = bv_hi(vd.w[j]);
+            oY.w[j] = bv_pack(g0 - d0, g1 - d1);
+            oR.w[j] = bv_pack(g0 + d0, g1 + d1);
+            const float y0v = bv_lo(oY.w[j]), y1v = bv_hi(oY.w[j]);
+            acc[0] += y0v + y1v;
+            acc[1] = fmaf(y0v, bv_lo(vy.w[j]), fmaf(y1v, bv_hi(vy.w[j]), acc[1]));
+            if (r) {
+                const float r0 = bv_lo(oR.w[j]), r1 = bv_hi(oR.w[j]);
+                acc[2] += r0 + r1;
+                acc[3] = fmaf(r0, bv_lo(vr.w[j]), fmaf(r1, bv_hi(vr.w[j]), acc[3]));
+            }
+        }
+        bv_st<VEC>(G + off, oY);
+        if (dr) bv_st<VEC>(dr + (long long)n * drns + (long long)c * TV + (long long)e * VEC, oR);
+    BV_WALK_END(TVv)
+    double* const dst[4] = {s1g, s2g, s1d, s2d};
+    flush_stats<4>(acc, dst, c);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+tcn_epilogue_fwd_vec_kernel(int N, int C, int TV, const bf16* __restrict__ u, long long uns, const float* __restrict__ su,
+                            const float* __restrict__ hu, int res_mode, const bf16* __restrict__ r, long long rns,
+                            const float* __restrict__ sr, const float* __restrict__ hr, int relu, bf16* __restrict__ out) {
+    const int c = blockIdx.x, TVv = TV / VEC;
+    const float a_u = su[c], b_u = hu[c];
+    const float a_r = (res_mode == TAMGCN_RES_AFFINE) ? sr[c] : 1.f;
+    const float b_r = (res_mode == TAMGCN_RES_AFFINE) ? hr[c] : 0.f;
+    BV_WALK_BEGIN(N, TVv)
+        const long long co = (long long)c * TV + (long long)e * VEC;
+        const BVec<VEC> vu = bv_ld<VEC>(u + (long long)n * uns + co);
+        BVec<VEC> vr, vo;
+        if (res_mode != TAMGCN_RES_NONE) vr = bv_ld<VEC>(r + (long long)n * rns + co);
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) {
+            float lo = fmaf(a_u, bv_lo(vu.w[j]), b_u), hi = fmaf(a_u, bv_hi(vu.w[j]), b_u);
+            if (res_mode != TAMGCN_RES_NONE) { lo += fmaf(a_r, bv_lo(vr.w[j]), b_r); hi += fmaf(a_r, bv_hi(vr.w[j]), b_r); }
+            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            vo.w[j] = bv_pack(lo, hi);
+        }
+        bv_st<VEC>(out + (long long)n * C * TV + co, vo);
+    BV_WALK_END(TVv)
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+tcn_epilogue_bwd_vec_kernel(int N, int C, int TV, const bf16* __restrict__ g, const bf16* __restrict__ out, int relu,
+                            const bf16* __restrict__ u, long long uns, const bf16* __restrict__ r, long long rns,
+                            bf16* __restrict__ G, double* s1, double* s2u, double* s2r) {
+    const int c = blockIdx.x, TVv = TV / VEC;
+    float acc[3] = {0.f, 0.f, 0.f};
+    BV_WALK_BEGIN(N, TVv)
+        const long long co = (long long)c * TV + (long long)e * VEC;
+        const long long off = (long long)n * C * TV + co;
+        BVec<VEC> vg = bv_ld<VEC>(g + off), vo, vr;
+        const BVec<VEC> vu = bv_ld<VEC>(u + (long long)n * uns + co);
+        if (relu) vo = bv_ld<VEC>(out + off);
+        if (r) vr = bv_ld<VEC>(r + (long long)n * rns + co);
+#pragma unroll
+        for (int j = 0; j < VEC / 2; ++j) {
+            float g0 = bv_lo(vg.w[j]), g1 = bv_hi(vg.w[j]);
+            if (relu) {
+                if (!(bv_lo(vo.w[j]) > 0.f)) g0 = 0.f;
+                if (!(bv_hi(vo.w[j]) > 0.f)) g1 = 0.f;
+                vg.w[j] = bv_pack(g0, g1);
+            }
+            acc[0] += g0 + g1;
+            acc[1] = fmaf(g0, bv_lo(vu.w[j]), fmaf(g1, bv_hi(vu.w[j]), acc[1]));
+            if (r) acc[2] = fmaf(g0, bv_lo(vr.w[j]), fmaf(g1, bv_hi(vr.w[j]), acc[2]));
+        }
+        if (G) bv_st<VEC>(G + off, vg);
+    BV_WALK_END(TVv)
+    double* const dst[3] = {s1, s2u, s2r};
+    flush_stats<3>(acc, dst, c);
+}
+
+// vector width usable for bf16 rows of TV elements: every pointer 2*VEC-byte aligned, every sample stride a multiple of VEC
+static inline int bv_width(int TV, std::initializer_list<const void*> ptrs, std::initializer_list<long long> strides) {
+    for (int v = 8; v >= 4; v >>= 1) {
+        bool ok = TV % v == 0;
+        for (const void* q : ptrs) ok = ok && (q == nullptr || (reinterpret_cast<uintptr_t>(q) & (uintptr_t)(2 * v - 1)) == 0);
+        for (long long st : strides) ok = ok && (st % v == 0);
+        if (ok) return v;
+    }
+    return 1;
+}
+static inline bool bv_disabled() {
+    static const int v = [] { const char* e = getenv("TAMGCN_DISABLE_VEC_EPI"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v == 1;
+}
+
 // MaxPool2d((3,1), stride (s,1), padding (1,0)) over the lazily transformed input
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -252,6 +457,15 @@ extern "C" int tamgcn_gcn_epilogue_fwd(int dtype, int N, int C, int TV, const vo
     TG_REQUIRE(res_mode != TAMGCN_RES_AFFINE || (sr && hr), "gcn_epilogue_fwd: residual coefficients missing");
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_BF16 && !bv_disabled()) {
+        const int vw = bv_width(TV, {y0, z, r, out}, {(long long)r_nstride});
+        if (vw > 1) {
+            if (vw == 8) gcn_epilogue_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)y0, sg, hg, (const bf16*)z, so, ho, res_mode, (const bf16*)r, r_nstride, sr, hr, (bf16*)out);
+            else gcn_epilogue_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)y0, sg, hg, (const bf16*)z, so, ho, res_mode, (const bf16*)r, r_nstride, sr, hr, (bf16*)out);
+            count_launch();
+            return check_launch("gcn_epilogue_fwd");
+        }
+    }
     if (dtype == TAMGCN_F32)
         gcn_epilogue_fwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)y0, sg, hg, (const float*)z, so, ho,
                                                              res_mode, (const float*)r, r_nstride, sr, hr, (float*)out);
@@ -270,6 +484,15 @@ extern "C" int tamgcn_gcn_epilogue_bwd(int dtype, int N, int C, int TV, const vo
                "gcn_epilogue_bwd: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_BF16 && !bv_disabled()) {
+        const int vw = bv_width(TV, {g, out, z, G, DZ}, {});
+        if (vw > 1) {
+            if (vw == 8) gcn_epilogue_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)g, (const bf16*)out, (const bf16*)z, so, ho, (bf16*)G, (bf16*)DZ, s1o, s2o);
+            else gcn_epilogue_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)g, (const bf16*)out, (const bf16*)z, so, ho, (bf16*)G, (bf16*)DZ, s1o, s2o);
+            count_launch();
+            return check_launch("gcn_epilogue_bwd");
+        }
+    }
     if (dtype == TAMGCN_F32)
         gcn_epilogue_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)g, (const float*)out,
                                                              (const float*)z, so, ho, (float*)G, (float*)DZ, s1o, s2o);
@@ -288,6 +511,15 @@ extern "C" int tamgcn_gcn_mid_bwd(int dtype, int N, int C, int TV, void* G, cons
     TG_REQUIRE(!r || (s1d && s2d), "gcn_mid_bwd: residual BN sums missing");
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_BF16 && !bv_disabled()) {
+        const int vw = bv_width(TV, {G, DD, dr, y0, r}, {(long long)dr_nstride, (long long)r_nstride});
+        if (vw > 1) {
+            if (vw == 8) gcn_mid_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride, (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d);
+            else gcn_mid_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride, (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d);
+            count_launch();
+            return check_launch("gcn_mid_bwd");
+        }
+    }
     if (dtype == TAMGCN_F32)
         gcn_mid_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (float*)G, (const float*)DD, (float*)dr, dr_nstride,
                                                         (const float*)y0, (const float*)r, r_nstride, s1g, s2g, s1d, s2d);
@@ -308,6 +540,15 @@ extern "C" int tamgcn_tcn_epilogue_fwd(int dtype, int N, int C, int TV, const vo
     TG_REQUIRE(res_mode != TAMGCN_RES_AFFINE || (sr && hr), "tcn_epilogue_fwd: residual coefficients missing");
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_BF16 && !bv_disabled()) {
+        const int vw = bv_width(TV, {u, r, out}, {(long long)u_nstride, (long long)r_nstride});
+        if (vw > 1) {
+            if (vw == 8) tcn_epilogue_fwd_vec_kernel<8><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)u, u_nstride, su, hu, res_mode, (const bf16*)r, r_nstride, sr, hr, relu, (bf16*)out);
+            else tcn_epilogue_fwd_vec_kernel<4><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)u, u_nstride, su, hu, res_mode, (const bf16*)r, r_nstride, sr, hr, relu, (bf16*)out);
+            count_launch();
+            return check_launch("tcn_epilogue_fwd");
+        }
+    }
     if (dtype == TAMGCN_F32)
         tcn_epilogue_fwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)u, u_nstride, su, hu, res_mode,
                                                              (const float*)r, r_nstride, sr, hr, relu, (float*)out);
@@ -327,6 +568,15 @@ extern "C" int tamgcn_tcn_epilogue_bwd(int dtype, int N, int C, int TV, const vo
     TG_REQUIRE(!r || s2r, "tcn_epilogue_bwd: residual BN sum missing");
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
+    if (dtype == TAMGCN_BF16 && !bv_disabled()) {
+        const int vw = bv_width(TV, {g, out, u, r, G}, {(long long)u_nstride, (long long)r_nstride});
+        if (vw > 1) {
+            if (vw == 8) tcn_epilogue_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)g, (const bf16*)out, relu, (const bf16*)u, u_nstride, (const bf16*)r, r_nstride, (bf16*)G, s1, s2u, s2r);
+            else tcn_epilogue_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(N, C, TV, (const bf16*)g, (const bf16*)out, relu, (const bf16*)u, u_nstride, (const bf16*)r, r_nstride, (bf16*)G, s1, s2u, s2r);
+            count_launch();
+            return check_launch("tcn_epilogue_bwd");
+        }
+    }
     if (dtype == TAMGCN_F32)
         tcn_epilogue_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (const float*)g, (const float*)out, relu,
                                                              (const float*)u, u_nstride, (const float*)r, r_nstride,
