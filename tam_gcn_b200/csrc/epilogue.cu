@@ -346,6 +346,110 @@ tcn_epilogue_bwd_vec_kernel(int N, int C, int TV, const bf16* __restrict__ g, co
     flush_stats<3>(acc, dst, c);
 }
 
+// lazy operand on 4 consecutive bf16 elements (8-byte accesses): f(a*p + b*q + c)
+__device__ __forceinline__ void bv_opnd4(const Opnd& o, const OpCoef& k, int n, long long off, float (&v)[4]) {
+    const BVec<4> p = bv_ld<4>((const bf16*)o.p + (long long)n * o.pns + off);
+    v[0] = k.a * bv_lo(p.w[0]) + k.c; v[1] = k.a * bv_hi(p.w[0]) + k.c;
+    v[2] = k.a * bv_lo(p.w[1]) + k.c; v[3] = k.a * bv_hi(p.w[1]) + k.c;
+    if (o.q) {
+        const BVec<4> q = bv_ld<4>((const bf16*)o.q + (long long)n * o.qns + off);
+        v[0] = fmaf(k.b, bv_lo(q.w[0]), v[0]); v[1] = fmaf(k.b, bv_hi(q.w[0]), v[1]);
+        v[2] = fmaf(k.b, bv_lo(q.w[1]), v[2]); v[3] = fmaf(k.b, bv_hi(q.w[1]), v[3]);
+    }
+    if (o.relu) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+}
+
+// max-pool forward, 4 joints per thread (V % 4 == 0): three 8-byte row loads per output vector
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec_kernel(int N, int C, int Tn, int To, int V, int s, Opnd x, bf16* __restrict__ y, long long yns, double* ssum,
+                       double* ssq) {
+    const int c = blockIdx.x, VQ = V / 4, TVv = To * VQ;
+    const OpCoef cf = opnd_coef(x, c);
+    float acc[2] = {0.f, 0.f};
+    BV_WALK_BEGIN(N, TVv)
+        const int to = e / VQ, vq = e - to * VQ;
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+            const int t = to * s - 1 + dt;
+            if (t >= 0 && t < Tn) {
+                float v[4];
+                bv_opnd4(x, cf, n, ((long long)c * Tn + t) * V + 4 * vq, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], v[j]);
+            }
+        }
+        BVec<4> o;
+        o.w[0] = bv_pack(best[0], best[1]); o.w[1] = bv_pack(best[2], best[3]);
+        bv_st<4>(y + (long long)n * yns + ((long long)c * To + to) * V + 4 * vq, o);
+        const float r0 = bv_lo(o.w[0]), r1 = bv_hi(o.w[0]), r2 = bv_lo(o.w[1]), r3 = bv_hi(o.w[1]);
+        acc[0] += (r0 + r1) + (r2 + r3);
+        acc[1] = fmaf(r0, r0, fmaf(r1, r1, fmaf(r2, r2, fmaf(r3, r3, acc[1]))));
+    BV_WALK_END(TVv)
+    double* const dst[2] = {ssum, ssq};
+    flush_stats<2>(acc, dst, c);
+}
+
+// max-pool backward, 4 joints per thread: the five input rows t-2..t+2 that any window containing t can touch are
+// loaded once (8 bytes each), then the (first) arg-max of each window is taken per joint exactly as above
+__global__ void __launch_bounds__(256)
+maxpool_bwd_vec_kernel(int N, int C, int Tn, int To, int V, int s, Opnd dy, Opnd x, bf16* __restrict__ dh, long long dhns,
+                       double* s1, double* s2) {
+    const int c = blockIdx.x, VQ = V / 4, TVv = Tn * VQ;
+    const OpCoef cf = opnd_coef(x, c), df = opnd_coef(dy, c);
+    float acc[2] = {0.f, 0.f};
+    BV_WALK_BEGIN(N, TVv)
+        const int t = e / VQ, vq = e - t * VQ;
+        const long long xoff = (long long)c * Tn * V + 4 * vq;
+        float xv[5][4];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const int tt = t - 2 + r;
+            if (tt >= 0 && tt < Tn) bv_opnd4(x, cf, n, xoff + (long long)tt * V, xv[r]);
+            else { xv[r][0] = xv[r][1] = xv[r][2] = xv[r][3] = -INFINITY; }
+        }
+        const BVec<4> pw = bv_ld<4>((const bf16*)x.p + (long long)n * x.pns + xoff + (long long)t * V);
+        const float pv[4] = {bv_lo(pw.w[0]), bv_hi(pw.w[0]), bv_lo(pw.w[1]), bv_hi(pw.w[1])};
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        int to_lo = (t - 1 + s - 1) / s;
+        if (t - 1 < 0) to_lo = 0;
+        const int to_hi = min(To - 1, (t + 1) / s);
+        for (int to = to_lo; to <= to_hi; ++to) {
+            float dyv[4];
+            bv_opnd4(dy, df, n, ((long long)c * To + to) * V + 4 * vq, dyv);
+            const int r0 = to * s - 1 - (t - 2);              // row index of the window's first row in xv (0..2)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float best = -INFINITY;
+                int arg = -1;
+#pragma unroll
+                for (int dt = 0; dt < 3; ++dt) {
+                    const int tt = to * s - 1 + dt;
+                    // xv is indexed with compile-time rows only (registers): select the row by comparing r0
+                    const float val = (r0 + dt == 0) ? xv[0][j] : (r0 + dt == 1) ? xv[1][j] : (r0 + dt == 2) ? xv[2][j]
+                                      : (r0 + dt == 3) ? xv[3][j] : xv[4][j];
+                    if (tt >= 0 && tt < Tn && val > best) { best = val; arg = tt; }
+                }
+                if (arg == t) d[j] += dyv[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (!(fmaf(cf.a, pv[j], cf.c) > 0.f)) d[j] = 0.f;
+        BVec<4> o;
+        o.w[0] = bv_pack(d[0], d[1]); o.w[1] = bv_pack(d[2], d[3]);
+        bv_st<4>(dh + (long long)n * dhns + xoff + (long long)t * V, o);
+        const float q0 = bv_lo(o.w[0]), q1 = bv_hi(o.w[0]), q2 = bv_lo(o.w[1]), q3 = bv_hi(o.w[1]);
+        acc[0] += (q0 + q1) + (q2 + q3);
+        acc[1] = fmaf(q0, pv[0], fmaf(q1, pv[1], fmaf(q2, pv[2], fmaf(q3, pv[3], acc[1]))));
+    BV_WALK_END(TVv)
+    double* const dst[2] = {s1, s2};
+    flush_stats<2>(acc, dst, c);
+}
+
 // vector width usable for bf16 rows of TV elements: every pointer 2*VEC-byte aligned, every sample stride a multiple of VEC
 static inline int bv_width(int TV, std::initializer_list<const void*> ptrs, std::initializer_list<long long> strides) {
     for (int v = 8; v >= 4; v >>= 1) {
@@ -598,6 +702,12 @@ extern "C" int tamgcn_maxpool_fwd(int dtype, int N, int C, int T, int To, int V,
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
     const Opnd xo = make_opnd(x);
+    if (dtype == TAMGCN_BF16 && !bv_disabled() && V % 4 == 0 &&
+        bv_width(4, {xo.p, xo.q, y}, {xo.pns, xo.q ? xo.qns : 0, (long long)y_nstride}) == 4) {
+        maxpool_fwd_vec_kernel<<<grid, 256, 0, st>>>(N, C, T, To, V, stride, xo, (bf16*)y, y_nstride, stat_sum, stat_sumsq);
+        count_launch();
+        return check_launch("maxpool_fwd");
+    }
     if (dtype == TAMGCN_F32)
         maxpool_fwd_kernel<float><<<grid, 256, 0, st>>>(N, C, T, To, V, stride, xo, (float*)y, y_nstride, stat_sum, stat_sumsq);
     else if (dtype == TAMGCN_BF16)
@@ -616,6 +726,12 @@ extern "C" int tamgcn_maxpool_bwd(int dtype, int N, int C, int T, int To, int V,
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
     const Opnd xo = make_opnd(x), dyo = make_opnd(dy);
+    if (dtype == TAMGCN_BF16 && !bv_disabled() && V % 4 == 0 &&
+        bv_width(4, {xo.p, xo.q, dyo.p, dyo.q, dh}, {xo.pns, xo.q ? xo.qns : 0, dyo.pns, dyo.q ? dyo.qns : 0, (long long)dh_nstride}) == 4) {
+        maxpool_bwd_vec_kernel<<<grid, 256, 0, st>>>(N, C, T, To, V, stride, dyo, xo, (bf16*)dh, dh_nstride, s1, s2);
+        count_launch();
+        return check_launch("maxpool_bwd");
+    }
     if (dtype == TAMGCN_F32)
         maxpool_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, T, To, V, stride, dyo, xo, (float*)dh, dh_nstride, s1, s2);
     else if (dtype == TAMGCN_BF16)
