@@ -344,6 +344,69 @@ int tconv_mma_fwd_dgrad(const tamgcn_conv_geom* g, int kind, const Opnd& in, con
 int tconv_mma_wgrad(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* db, cudaStream_t st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 1x1 convolutions over a handful of positions per sample (the conv1 / conv2 branches of CTRGC act on the
+// T-mean of x: L = V positions, models/ctrgcn.py:173): fp32, plain operands.  The 64 x 64 tiles above would be
+// two thirds empty and walk K in 16-wide steps with two barriers each; here the sample's whole input sits in shared
+// memory and every thread owns a few outputs.
+// ------------------------------------------------------------------------------------------------
+#define SL_OT 24      // output channels per CTA (forward)
+#define SL_CT 32      // input channels per CTA (data gradient)
+
+// y[n,o,l] = sum_c W[o,c] x[n,c,l] + b[o]
+__global__ void __launch_bounds__(256)
+conv1x1_smallL_fwd_kernel(int Cin, int Cout, int L, const float* __restrict__ x, long long xns, const float* __restrict__ W,
+                          const float* __restrict__ bias, float* __restrict__ y, long long yns) {
+    extern __shared__ __align__(16) float sl_xs[];             // [Cin][L]
+    const int n = blockIdx.x, o0 = blockIdx.y * SL_OT;
+    const float* xn = x + (long long)n * xns;
+    for (int i = threadIdx.x; i < Cin * L; i += blockDim.x) sl_xs[i] = __ldg(xn + i);
+    __syncthreads();
+    const int no = min(SL_OT, Cout - o0);
+    for (int idx = threadIdx.x; idx < no * L; idx += blockDim.x) {
+        const int o = idx / L, l = idx - o * L;
+        const float* w = W + (long long)(o0 + o) * Cin;
+        float acc = bias ? __ldg(bias + o0 + o) : 0.f;
+        int c = 0;
+        if ((Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+            for (; c < Cin; c += 4) {
+                const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c));
+                acc = fmaf(wv.x, sl_xs[c * L + l], acc);
+                acc = fmaf(wv.y, sl_xs[(c + 1) * L + l], acc);
+                acc = fmaf(wv.z, sl_xs[(c + 2) * L + l], acc);
+                acc = fmaf(wv.w, sl_xs[(c + 3) * L + l], acc);
+            }
+        }
+        for (; c < Cin; ++c) acc = fmaf(__ldg(w + c), sl_xs[c * L + l], acc);
+        y[(long long)n * yns + (long long)(o0 + o) * L + l] = acc;
+    }
+}
+
+// dx[n,c,l] = sum_o W[o,c] dy[n,o,l]
+__global__ void __launch_bounds__(256)
+conv1x1_smallL_dgrad_kernel(int Cin, int Cout, int L, const float* __restrict__ dy, long long dyns,
+                            const float* __restrict__ W, float* __restrict__ dx, long long dxns) {
+    extern __shared__ __align__(16) float sl_ds[];             // [Cout][L]
+    const int n = blockIdx.x, c0 = blockIdx.y * SL_CT;
+    const float* dn = dy + (long long)n * dyns;
+    for (int i = threadIdx.x; i < Cout * L; i += blockDim.x) sl_ds[i] = __ldg(dn + i);
+    __syncthreads();
+    const int nc = min(SL_CT, Cin - c0);
+    for (int idx = threadIdx.x; idx < nc * L; idx += blockDim.x) {
+        const int l = idx / nc, c = idx - l * nc;             // consecutive threads: consecutive c (coalesced rows of W)
+        const float* w = W + c0 + c;
+        float acc = 0.f;
+#pragma unroll 4
+        for (int o = 0; o < Cout; ++o) acc = fmaf(__ldg(w + (long long)o * Cin), sl_ds[o * L + l], acc);
+        dx[(long long)n * dxns + (long long)(c0 + c) * L + l] = acc;
+    }
+}
+
+static inline bool opnd_is_plain(const Opnd& o) { return !o.a && !o.b && !o.c && !o.q && !o.relu; }
+static inline bool small_l_geom(const ConvP& p) {
+    return p.k == 1 && p.s == 1 && p.p == 0 && p.T == p.To && p.T * p.V <= 32 && p.N <= 65535;
+}
+
 extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgcn_operand* x, const float* W,
                                const void* wpack, const float* bias, void* y, int64_t y_nstride, double* stat_sum,
                                double* stat_sumsq, int stat_c0, tamgcn_stream stream) {
@@ -358,6 +421,13 @@ extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgc
         if (rc != 0) return rc < 0 ? rc : 0;
         rc = conv_fwd_tc(g, xo, wpack, bias, y, y_nstride, stat_sum, stat_sumsq, stat_c0, st);
         if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    if (dtype == TAMGCN_F32 && small_l_geom(p) && opnd_is_plain(xo) && !stat_sum && (size_t)p.Cin * p.T * p.V * 4 <= 48 * 1024) {
+        const int L = p.T * p.V;
+        conv1x1_smallL_fwd_kernel<<<dim3(p.N, cdiv(p.Cout, SL_OT)), 256, (size_t)p.Cin * L * 4, st>>>(
+            p.Cin, p.Cout, L, (const float*)xo.p, xo.pns, W, bias, (float*)y, y_nstride);
+        count_launch();
+        return check_launch("conv_fwd(small L)");
     }
     dim3 grid(cdiv((long long)p.To * p.V, TN), cdiv(p.Cout, TM), p.N);
     if (dtype == TAMGCN_F32) {
@@ -391,6 +461,14 @@ extern "C" int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tam
         rc = conv_dgrad_tc(g, dyo, wpack, dx, dx_nstride, addend, addend_nstride, bcast, bcast_scale,
                            mask ? &mo : nullptr, s1, s2, st);
         if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    if (dtype == TAMGCN_F32 && small_l_geom(p) && opnd_is_plain(dyo) && !addend && !bcast && !mask && !s1 &&
+        (size_t)p.Cout * p.T * p.V * 4 <= 48 * 1024) {
+        const int L = p.T * p.V;
+        conv1x1_smallL_dgrad_kernel<<<dim3(p.N, cdiv(p.Cin, SL_CT)), 256, (size_t)p.Cout * L * 4, st>>>(
+            p.Cin, p.Cout, L, (const float*)dyo.p, dyo.pns, W, (float*)dx, dx_nstride);
+        count_launch();
+        return check_launch("conv_dgrad(small L)");
     }
     dim3 grid(cdiv((long long)p.T * p.V, TN), cdiv(p.Cin, TM), p.N);
     if (dtype == TAMGCN_F32) {

@@ -130,6 +130,28 @@ def test_conv_dgrad(dt, geom, V, opts):
         assert rel(outs[0][1], outs[1][1]) < tol(dt)
 
 
+@pytest.mark.parametrize('Cin,Cout,V', [(64, 48, 20), (256, 192, 20), (3, 16, 20), (128, 96, 25), (70, 50, 25)])
+def test_conv_small_l(Cin, Cout, V):
+    """fp32 1x1 convs over a handful of positions per sample (CTRGC conv1 / conv2 on the T-mean): dedicated kernels."""
+    _dev()
+    from tam_gcn_b200 import ops
+    N = 5
+    g = gen(11)
+    x = rnd(g, N, Cin, 1, V)
+    dy = rnd(g, N, Cout, 1, V)
+    W = rnd(g, Cout, Cin, scale=Cin ** -0.5)
+    b = rnd(g, Cout)
+    outs = []
+    for fwd, dgrad, conv in ((ops.conv_fwd, ops.conv_dgrad, real_opnd), (E.conv_fwd, E.conv_dgrad, lambda o: o)):
+        y = torch.zeros(N, Cout, 1, V, device='cuda')
+        dx = torch.zeros(N, Cin, 1, V, device='cuda')
+        fwd(conv(E.Opnd(x)), W, b, y)
+        dgrad(conv(E.Opnd(dy)), W, dx)
+        outs.append((y, dx))
+    assert rel(outs[0][0], outs[1][0]) < 1e-5
+    assert rel(outs[0][1], outs[1][1]) < 1e-5
+
+
 @pytest.mark.parametrize('dt,geom,V', [(dt, gm, V) for dt in DT for gm in CONV_GEOMS for V in (20, 25)])
 def test_conv_wgrad(dt, geom, V):
     _dev()
