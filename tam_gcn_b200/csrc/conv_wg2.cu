@@ -129,7 +129,7 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
         const int lga = ga == 8 ? 3 : 2, lgb = gb == 8 ? 3 : 2;      // log2(units per row): 8 -> 8 units, 4 -> 16 units
         const int sha = 6 - lga, shb = 6 - lgb;                      // idx >> sh = row
         const int lag = p.lag;
-        int u0 = 0, u1 = 0, u2 = 0;                                   // chunk ids in flight, newest first
+        int u0 = 0, u1 = 0, u2 = 0, u3 = 0, u4 = 0;                   // chunk ids in flight, newest first
         // source offset of a B unit or -1
         auto b_src = [&](int j, int pos) -> int {
             if (pos >= Lout) return -1;
@@ -140,7 +140,7 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
         };
         auto retire = [&](int age, int newest) {
             int sp = newest - age; if (sp < 0) sp += S;
-            const int u = age == 0 ? u0 : (age == 1 ? u1 : u2);
+            const int u = age == 0 ? u0 : (age == 1 ? u1 : (age == 2 ? u2 : (age == 3 ? u3 : u4)));
             const int n = u / p.nchunk, pos0 = (u - n * p.nchunk) * 64;
             const uint32_t sA = s0 + (uint32_t)sp * p.stage_bytes, sB = sA + p.a_bytes + p.aq_bytes;
             if (a_lazy) {
@@ -205,9 +205,10 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
                 }
             }
             w2_commit();
-            u2 = u1; u1 = u0; u0 = u;
+            u4 = u3; u3 = u2; u2 = u1; u1 = u0; u0 = u;
             if (cnt >= lag) {
-                if (lag == 2) w2_wait_group<2>(); else if (lag == 1) w2_wait_group<1>(); else w2_wait_group<0>();
+                if (lag == 4) w2_wait_group<4>(); else if (lag == 3) w2_wait_group<3>();
+                else if (lag == 2) w2_wait_group<2>(); else if (lag == 1) w2_wait_group<1>(); else w2_wait_group<0>();
                 retire(lag, stg);
             }
             if (++stg == S) { stg = 0; ph ^= 1; }
@@ -328,7 +329,10 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     if (szH + szC + 2 * p.stage_bytes > budget) return 0;
     p.S = (int)((budget - szH - szC) / p.stage_bytes);
     if (p.S > W2_SMAX) p.S = W2_SMAX;
-    p.lag = p.S >= 4 ? 2 : (p.S == 3 ? 1 : 0);
+    // chunks of cp.async in flight beyond the one being issued: at training batch sizes a CTA streams only a handful of
+    // chunks and each costs a full L2 round trip, so the pipeline runs as deep as the stages allow
+    p.lag = p.S >= 6 ? 4 : (p.S == 5 ? 3 : (p.S == 4 ? 2 : (p.S == 3 ? 1 : 0)));
+    { static const int lmax = [] { const char* e = getenv("TAMGCN_W2_LAG"); return e ? atoi(e) : 4; }(); if (p.lag > lmax) p.lag = lmax; }
     p.off_hdr = (uint32_t)p.S * p.stage_bytes;
     p.off_coef = p.off_hdr + szH;
     const size_t sm = (size_t)p.off_coef + szC + 1024;
