@@ -201,8 +201,8 @@ def ctrgc_roofline(dtype, peak_gbs, peak_src):
     ms = e0.elapsed_time(e1) / iters
     ach = alg / (ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, ncu --set full
-    # (profiles/r01o_ctrgc_tc3_full.txt: 826.36 MB read + 251.89 MB written)
-    traffic = 1078249216 if dtype == torch.bfloat16 else None
+    # (profiles/r01s_ctrgc_tc3_full.txt: 826.36 MB read + 252.31 MB written)
+    traffic = 1078670080 if dtype == torch.bfloat16 else None
     return dict(bound='hbm', kernel='ctrgc_fwd_tc3_kernel (tcgen05 + mma.sync)' if dtype == torch.bfloat16 else 'ctrgc_fwd_kernel',
                 achieved=ach, peak=peak_gbs, unit='GB/s', frac=ach / peak_gbs,
                 traffic=traffic, peak_source=peak_src, algorithmic_bytes=alg, ms_per_launch=ms,
