@@ -245,18 +245,30 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
         const int q = warp & 3, grp = warp >> 2;          // lane quarter, one of three warps sharing it
         const int row = q * 32 + lane;
         const int CK = g.Cin * k, nblk = (k * NTp + 15) >> 4;
-        for (int b = grp; b < nblk; b += 3) {
+        // All split-K CTAs of a (co, ci) tile finish at about the same time and add into the same dW entries: walked in the
+        // same order, every address would take gridDim.z back-to-back atomics (measured: the drain was a quarter of the
+        // kernel).  Each CTA therefore starts at its own column block and column quarter.
+        const int rot_b = (int)(blockIdx.z % (unsigned)nblk), rot_c = (int)((blockIdx.z / (unsigned)nblk) & 3u);
+#define W2_DRAIN_COLS(R)                                                                                          \
+    _Pragma("unroll") for (int c0 = 0; c0 < 16; ++c0) {                                                          \
+        const int c = (c0 + (R)) & 15;                                                                            \
+        const int col = b * 16 + c, j = col / NTp, ci = col - j * NTp;                                            \
+        if (j < k && ci < nci) atomicAdd(dW + (long long)(co0 + row) * CK + (ci0 + ci) * k + j, acc[c]);          \
+        else if (do_bias && j == 0 && ci == NT) atomicAdd(dbias + co0 + row, acc[c]);                             \
+    }
+        for (int bb = grp; bb < nblk; bb += 3) {
+            int b = bb + rot_b;
+            if (b >= nblk) b -= nblk;
             float acc[16];
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 16), acc);
             if (row < nco && !hdr->error) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int col = b * 16 + c, j = col / NTp, ci = col - j * NTp;
-                    if (j < k && ci < nci) atomicAdd(dW + (long long)(co0 + row) * CK + (ci0 + ci) * k + j, acc[c]);
-                    else if (do_bias && j == 0 && ci == NT) atomicAdd(dbias + co0 + row, acc[c]);
-                }
+                if (rot_c == 0) { W2_DRAIN_COLS(0) }
+                else if (rot_c == 1) { W2_DRAIN_COLS(4) }
+                else if (rot_c == 2) { W2_DRAIN_COLS(8) }
+                else { W2_DRAIN_COLS(12) }
             }
         }
+#undef W2_DRAIN_COLS
     }
     tc_fence_before();
     __syncthreads();

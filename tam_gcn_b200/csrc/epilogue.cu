@@ -414,23 +414,23 @@ maxpool_bwd_vec_kernel(int N, int C, int Tn, int To, int V, int s, Opnd dy, Opnd
         const BVec<4> pw = bv_ld<4>((const bf16*)x.p + (long long)n * x.pns + xoff + (long long)t * V);
         const float pv[4] = {bv_lo(pw.w[0]), bv_hi(pw.w[0]), bv_lo(pw.w[1]), bv_hi(pw.w[1])};
         float d[4] = {0.f, 0.f, 0.f, 0.f};
-        int to_lo = (t - 1 + s - 1) / s;
-        if (t - 1 < 0) to_lo = 0;
-        const int to_hi = min(To - 1, (t + 1) / s);
-        for (int to = to_lo; to <= to_hi; ++to) {
+        // a window containing t starts at row t-2, t-1 or t (xv rows r0 = 0, 1, 2): compile-time register indices
+#pragma unroll
+        for (int r0 = 0; r0 < 3; ++r0) {
+            const int tt0 = t - 2 + r0;                        // first row of the window = to * s - 1
+            if ((tt0 + 1) % s != 0) continue;
+            const int to = (tt0 + 1) / s;
+            if (tt0 + 1 < 0 || to >= To) continue;
             float dyv[4];
             bv_opnd4(dy, df, n, ((long long)c * To + to) * V + 4 * vq, dyv);
-            const int r0 = to * s - 1 - (t - 2);              // row index of the window's first row in xv (0..2)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float best = -INFINITY;
                 int arg = -1;
 #pragma unroll
                 for (int dt = 0; dt < 3; ++dt) {
-                    const int tt = to * s - 1 + dt;
-                    // xv is indexed with compile-time rows only (registers): select the row by comparing r0
-                    const float val = (r0 + dt == 0) ? xv[0][j] : (r0 + dt == 1) ? xv[1][j] : (r0 + dt == 2) ? xv[2][j]
-                                      : (r0 + dt == 3) ? xv[3][j] : xv[4][j];
+                    const int tt = tt0 + dt;
+                    const float val = xv[r0 + dt][j];
                     if (tt >= 0 && tt < Tn && val > best) { best = val; arg = tt; }
                 }
                 if (arg == t) d[j] += dyv[j];
