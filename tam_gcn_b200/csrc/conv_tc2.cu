@@ -603,6 +603,28 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
     int tps = (p.Lout + nmax - 1) / nmax;
     int NT = (((p.Lout + tps - 1) / tps) + 15) & ~15;
     if (NT < 16) NT = 16;
+    {
+        // Wave quantisation: the persistent CTAs of an output-channel group share N * tps tiles; with a few tiles per CTA
+        // the last, partly filled round costs as much as a full one.  Among tile widths up to the TMEM limit pick the one
+        // with the smallest (rounds x (tile width + a fixed per-tile cost)).
+        static const int ovh = [] { const char* e = getenv("TAMGCN_C2_TILE_OVH"); return e ? atoi(e) : 64; }();
+        if (ovh >= 0) {
+            const long long per_oct = c2_num_sms() / ((p.MT_total + 1) / 2) > 0 ? c2_num_sms() / ((p.MT_total + 1) / 2) : 1;
+            long long best = -1;
+            int bestNT = NT;
+            for (int cand = tps; cand <= tps + 12; ++cand) {
+                int nt = (((p.Lout + cand - 1) / cand) + 15) & ~15;
+                if (nt < 16) nt = 16;
+                if (nt > nmax) continue;
+                const long long tiles_c = (long long)g.N * ((p.Lout + nt - 1) / nt);
+                const long long rounds = (tiles_c + per_oct - 1) / per_oct;
+                const long long cost = rounds * (nt + ovh);
+                if (best < 0 || cost < best) { best = cost; bestNT = nt; }
+                if (nt == 16) break;
+            }
+            NT = bestNT;
+        }
+    }
     p.NT = NT;
     p.tps = (p.Lout + NT - 1) / NT;
     p.NTp = (NT + 31) & ~31;
