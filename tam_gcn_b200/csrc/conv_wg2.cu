@@ -25,7 +25,7 @@ struct ConvP {
 struct W2P {
     ConvP g;
     int Lin, Lout, NT, NTp, nchunk, units;
-    int gran_a, gran_b, fast, S, lag, tmem_cols, has_bias;
+    int gran_a, gran_b, fast, S, lag, tmem_cols, has_bias, flat;
     uint32_t a_bytes, aq_bytes, b_bytes, bq_bytes, stage_bytes, off_hdr, off_coef;
 };
 
@@ -138,17 +138,27 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
             const int t = tq * g.s + j * g.d - g.p;
             return (t >= 0 && t < g.T) ? t * g.V + v : -1;
         };
+        // A chunk is 64 consecutive positions.  Per-sample chunking wastes most of the last chunk of every sample when
+        // T*V is just above a multiple of 64 (260 -> 5 chunks for 4.06); for 1x1 stride-1 convolutions the chunks tile the
+        // flat (sample, position) axis instead and a chunk may continue into the next sample (p.flat; T*V >= 64, T*V a
+        // multiple of the copy granularity, so no unit straddles the boundary).
+        auto chunk_origin = [&](int u, int& n, int& pos0) {
+            if (p.flat) { const long long f0 = (long long)u * 64; n = (int)(f0 / Lout); pos0 = (int)(f0 - (long long)n * Lout); }
+            else { n = u / p.nchunk; pos0 = (u - n * p.nchunk) * 64; }
+        };
+        auto unit_valid = [&](int n, int pos) -> bool { return p.flat ? (n + (pos >= Lout ? 1 : 0) < g.N) : (pos < Lout); };
         auto retire = [&](int age, int newest) {
             int sp = newest - age; if (sp < 0) sp += S;
             const int u = age == 0 ? u0 : (age == 1 ? u1 : (age == 2 ? u2 : (age == 3 ? u3 : u4)));
-            const int n = u / p.nchunk, pos0 = (u - n * p.nchunk) * 64;
+            int n, pos0;
+            chunk_origin(u, n, pos0);
             const uint32_t sA = s0 + (uint32_t)sp * p.stage_bytes, sB = sA + p.a_bytes + p.aq_bytes;
             if (a_lazy) {
                 const int tot = nco << sha;
 #pragma unroll 1
                 for (int idx = tid; idx < tot; idx += W2_PR_T) {
                     const int r = idx >> sha, pu = (idx & (upa - 1)) * ga;
-                    if (pos0 + pu >= Lout) continue;
+                    if (!unit_valid(n, pos0 + pu)) continue;
                     const uint32_t ud = sA + w2_off((uint32_t)r, (uint32_t)pu);
                     if (ga == 8) w2_xform<8>(ud, ud + p.a_bytes, a_q, coefA[r], coefA[128 + r], coefA[256 + r], dyo.relu);
                     else w2_xform<4>(ud, ud + p.a_bytes, a_q, coefA[r], coefA[128 + r], coefA[256 + r], dyo.relu);
@@ -160,7 +170,7 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
                 for (int idx = tid; idx < tot; idx += W2_PR_T) {
                     const int j = idx / per, i2 = idx - j * per;
                     const int r = i2 >> shb, pu = (i2 & (upb - 1)) * gb;
-                    if (b_src(j, pos0 + pu) < 0) continue;
+                    if (p.flat ? !unit_valid(n, pos0 + pu) : (b_src(j, pos0 + pu) < 0)) continue;
                     const uint32_t ud = sB + (uint32_t)(j * NTp) * 128u + w2_off((uint32_t)r, (uint32_t)pu);
                     if (gb == 8) w2_xform<8>(ud, ud + p.b_bytes, b_q, coefB[r], coefB[NT + r], coefB[2 * NT + r], xo.relu);
                     else w2_xform<4>(ud, ud + p.b_bytes, b_q, coefB[r], coefB[NT + r], coefB[2 * NT + r], xo.relu);
@@ -171,7 +181,8 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
         };
         int stg = 0, ph = 0, cnt = 0;
         for (int u = blockIdx.z; u < p.units; u += gridDim.z, ++cnt) {
-            const int n = u / p.nchunk, pos0 = (u - n * p.nchunk) * 64;
+            int n, pos0;
+            chunk_origin(u, n, pos0);
             if (!mbar_wait(&hdr->empty[stg], (uint32_t)(ph ^ 1))) hdr->error = 1;
             const uint32_t sA = s0 + (uint32_t)stg * p.stage_bytes, sB = sA + p.a_bytes + p.aq_bytes;
             {   // A: dY rows
@@ -181,11 +192,13 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
 #pragma unroll 1
                 for (int idx = tid; idx < tot; idx += W2_PR_T) {
                     const int r = idx >> sha, pu = (idx & (upa - 1)) * ga;
-                    const bool ok = pos0 + pu < Lout;
+                    const bool ok = unit_valid(n, pos0 + pu);
+                    const bool nxt = p.flat && pos0 + pu >= Lout;           // the unit lies in sample n + 1
                     const long long e = ok ? (long long)r * Lout + pu : 0;
+                    const long long ep = (ok && nxt) ? e + dyo.pns - Lout : e, eq = (ok && nxt) ? e + dyo.qns - Lout : e;
                     const uint32_t dst = sA + w2_off((uint32_t)r, (uint32_t)pu);
-                    if (ga == 8) { w2_cp16(dst, pn + e, ok ? 16u : 0u); if (a_q) w2_cp16(dst + p.a_bytes, qn + e, ok ? 16u : 0u); }
-                    else { w2_cp8(dst, pn + e, ok ? 8u : 0u); if (a_q) w2_cp8(dst + p.a_bytes, qn + e, ok ? 8u : 0u); }
+                    if (ga == 8) { w2_cp16(dst, pn + ep, ok ? 16u : 0u); if (a_q) w2_cp16(dst + p.a_bytes, qn + eq, ok ? 16u : 0u); }
+                    else { w2_cp8(dst, pn + ep, ok ? 8u : 0u); if (a_q) w2_cp8(dst + p.a_bytes, qn + eq, ok ? 8u : 0u); }
                 }
             }
             {   // B_j: X rows shifted by tap j
@@ -196,12 +209,14 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
                 for (int idx = tid; idx < tot; idx += W2_PR_T) {
                     const int j = idx / per, i2 = idx - j * per;
                     const int r = i2 >> shb, pu = (i2 & (upb - 1)) * gb;
-                    const int off = b_src(j, pos0 + pu);
-                    const bool ok = off >= 0;
+                    const bool nxt = p.flat && pos0 + pu >= Lout;
+                    const int off = p.flat ? pos0 + pu : b_src(j, pos0 + pu);
+                    const bool ok = p.flat ? unit_valid(n, pos0 + pu) : off >= 0;
                     const long long e = ok ? (long long)r * Lin + off : 0;
+                    const long long ep = (ok && nxt) ? e + xo.pns - Lin : e, eq = (ok && nxt) ? e + xo.qns - Lin : e;
                     const uint32_t dst = sB + (uint32_t)(j * NTp) * 128u + w2_off((uint32_t)r, (uint32_t)pu);
-                    if (gb == 8) { w2_cp16(dst, pn + e, ok ? 16u : 0u); if (b_q) w2_cp16(dst + p.b_bytes, qn + e, ok ? 16u : 0u); }
-                    else { w2_cp8(dst, pn + e, ok ? 8u : 0u); if (b_q) w2_cp8(dst + p.b_bytes, qn + e, ok ? 8u : 0u); }
+                    if (gb == 8) { w2_cp16(dst, pn + ep, ok ? 16u : 0u); if (b_q) w2_cp16(dst + p.b_bytes, qn + eq, ok ? 16u : 0u); }
+                    else { w2_cp8(dst, pn + ep, ok ? 8u : 0u); if (b_q) w2_cp8(dst + p.b_bytes, qn + eq, ok ? 8u : 0u); }
                 }
             }
             w2_commit();
@@ -319,7 +334,9 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     p.NTp = (NT + 1 + 15) & ~15;
     p.tmem_cols = (int)tmem_cols_pow2((uint32_t)(g.k * p.NTp));
     p.nchunk = (p.Lout + 63) / 64;
-    const long long units = (long long)g.N * p.nchunk;
+    static const int flat_env = [] { const char* e = getenv("TAMGCN_W2_FLAT"); return e ? atoi(e) : 1; }();
+    p.flat = (flat_env && p.fast && p.Lout >= 64 && p.Lout % 64 != 0) ? 1 : 0;
+    const long long units = p.flat ? ((long long)g.N * p.Lout + 63) / 64 : (long long)g.N * p.nchunk;
     if (units > 0x7fffffffLL) return 0;
     p.units = (int)units;
     p.a_bytes = 16384u;
