@@ -381,6 +381,25 @@ static bool tm_setup(TmP& p, const tamgcn_conv_geom* g, int kind, size_t& smem) 
     int tps = (256 + p.N - 1) / p.N;
     if (tps < 1) tps = 1;
     if (tps > p.Tout) tps = p.Tout;
+    if (kind == 2) {
+        // weight gradient: a persistent grid of one CTA per SM walks N * tps units; pick the time blocking with the fewest
+        // (rounds x input rows per unit) — longer blocks amortise the tap halo and avoid a second, mostly empty round
+        static const int wg_search = [] { const char* e = getenv("TAMGCN_TCONV_WG_SEARCH"); return e ? atoi(e) : 1; }();
+        if (wg_search) {
+            long long best = -1;
+            int best_tps = tps;
+            for (int cand = 1; cand <= 16 && cand <= p.Tout; ++cand) {
+                const int TB = (p.Tout + cand - 1) / cand, RIN = (TB - 1) * p.s + 1 + (omax - omin);
+                const size_t sm_c = (size_t)CB * tm_oddpitch(((TB * NTW + 1) / 2) * 16) * 2 + (size_t)CB * tm_oddpitch(RIN * p.VP) * 2 + 6 * CB * 4;
+                if (sm_c > 100 * 1024) continue;
+                const long long units = (long long)p.N * ((p.Tout + TB - 1) / TB);
+                const long long rounds = (units + tm_num_sms() - 1) / tm_num_sms();
+                const long long cost = rounds * (RIN + 4);
+                if (best < 0 || cost < best) { best = cost; best_tps = cand; }
+            }
+            tps = best_tps;
+        }
+    }
     for (;;) {
         p.TB = (p.Tout + tps - 1) / tps;
         p.RIN = (p.TB - 1) * p.s + 1 + (omax - omin);
