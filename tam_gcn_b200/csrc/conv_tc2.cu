@@ -671,6 +671,10 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
         const double epi_work = 6.0 * (p.OC < 256 ? p.OC : 256), prod_work = (plain ? 1.5 : (xo.q ? 14.0 : 9.0)) * p.KT;
         p.n_epi = 8;
         if (nw >= 24 && epi_work > prod_work) p.n_epi = 16;
+        // K-heavy shapes (conv3 data gradient: K = 3 Cout, lazy two-tensor operand): the MMA warp waits on the producers
+        // for most of a tile while the epilogue runs once per 3-16 chunks: one epilogue warp per TMEM lane quarter.
+        static const double epi4 = [] { const char* e = getenv("TAMGCN_C2_EPI4"); return e ? atof(e) : 2.5; }();
+        if (epi4 > 0 && prod_work > epi4 * epi_work) p.n_epi = 4;
     }
 #define C2_LAUNCH(PL, EX)                                                                                              \
     do {                                                                                                               \
