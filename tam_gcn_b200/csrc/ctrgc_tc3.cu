@@ -28,8 +28,8 @@
 namespace tamgcn {
 
 #define C3_EPI_T 256
-#define C3_MMA_W 8
-#define C3_LD_T0 288
+#define C3_MMA_W 14
+#define C3_LD_T0 256
 #define C3_LD_T 128
 #define C3_Q_T0 416
 #define C3_Q_T 160
@@ -194,10 +194,8 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
 #pragma unroll
                 for (int j = 0; j < 20; j += 4) {
                     const uint32_t w0 = pack_bf16(acc[j], acc[j + 1]), w1 = pack_bf16(acc[j + 2], acc[j + 3]);
-                    const float f0 = __uint_as_float(w0 << 16), f1 = __uint_as_float(w0 & 0xffff0000u);
-                    const float f2 = __uint_as_float(w1 << 16), f3 = __uint_as_float(w1 & 0xffff0000u);
-                    s += (f0 + f1) + (f2 + f3);
-                    q = fmaf(f0, f0, q); q = fmaf(f1, f1, q); q = fmaf(f2, f2, q); q = fmaf(f3, f3, q);
+                    s += (acc[j] + acc[j + 1]) + (acc[j + 2] + acc[j + 3]);
+                    q = fmaf(acc[j], acc[j], q); q = fmaf(acc[j + 1], acc[j + 1], q); q = fmaf(acc[j + 2], acc[j + 2], q); q = fmaf(acc[j + 3], acc[j + 3], q);
                     c3_sts64(oa + j * 2, w0, w1);
                 }
             }
@@ -266,7 +264,7 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
                 if (++s == S) { s = 0; ph ^= 1; }
             }
         }
-    } else if (tid < C3_Q_T0) {
+    } else if (warp >= 8 && warp < 12) {
         // =============================== x3 loaders ===============================
         const int lt = tid - C3_LD_T0;
         const int lag = S >= 4 ? 2 : S - 2;                    // tiles of cp.async in flight beyond the current one
@@ -333,8 +331,9 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
         for (int it = max(nt - lag, 0); it < nt; ++it) mbar_arrive(&hdr->a_full[it % S]);
     } else {
         // =============================== topology builders ===============================
-        const int qt = tid - C3_Q_T0;                          // 0..159; warp bw owns the four u of group bw
-        const int bw = qt >> 5, gid = lane >> 2, tig = lane & 3;
+        // builder warps 12, 13, 15, 16, 17 (warp 14 issues the MMAs: it shares its scheduler with three warps, not four)
+        const int bw = warp < 14 ? warp - 12 : warp - 13, gid = lane >> 2, tig = lane & 3;
+        const int qt = bw * 32 + lane;                         // 0..159; warp bw owns the four u of group bw
         const int sel = gid & 3, cc = gid >> 2;                // MMA row gid = (channel cc, u-select sel); row gid+8 = channel cc+2
         const int u0 = 4 * bw, u = u0 + sel;
         const float alpha = __ldg(alpha_p);
