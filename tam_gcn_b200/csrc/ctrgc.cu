@@ -13,6 +13,7 @@
 //
 // SIMT fp32 math for both storage types.  V is a template parameter (20 = NW-UCLA, 25 = NTU).
 #include "common.cuh"
+#include <type_traits>
 #include "rows.cuh"
 #include <atomic>
 #include <cstdlib>
@@ -47,12 +48,31 @@ struct CtrgcP {
     long long x3ns, x12ns, yns;
 };
 
-// D_i -> shared (pitch DP); also used by the backward kernel
-template <int V, int DP>
-__device__ __forceinline__ void build_D(float* Ds, const float* __restrict__ x1, const float* __restrict__ x2, int R) {
-    for (int idx = threadIdx.x; idx < R * V * V; idx += blockDim.x) {
-        const int r = idx / (V * V), rem = idx - r * V * V, u = rem / V, v = rem - u * V;
-        Ds[(r * V + u) * DP + v] = tanhf(__ldg(x1 + r * V + u) - __ldg(x2 + r * V + v));
+// D_i -> shared (pitch DP); also used by the backward kernel.  FAST (bf16 activations): hardware tanh.approx (2^-11
+// relative, below the bf16 rounding of everything downstream) instead of the ~30-instruction tanhf — every CTA of a
+// sample rebuilds the same R*V*V table, which made this the whole cost of the kernel at R = 32.
+template <int V, int DP, bool FAST>
+__device__ __forceinline__ void build_D(float* Ds, float* xs, const float* __restrict__ x1, const float* __restrict__ x2, int R) {
+    // x1 / x2 of the plane -> shared once; then one (r, u) row of V values per thread: no divisions or global loads per
+    // element (every CTA of a sample rebuilds this table, so its cost is multiplied by Cout / CT)
+    for (int idx = threadIdx.x; idx < R * V; idx += blockDim.x) {
+        xs[idx] = __ldg(x1 + idx);
+        xs[R * V + idx] = __ldg(x2 + idx);
+    }
+    __syncthreads();
+    for (int task = threadIdx.x; task < R * V; task += blockDim.x) {
+        const int r = task / V;
+        const float a = xs[task];
+        const float* b = xs + R * V + r * V;
+        float* d = Ds + (size_t)task * DP;
+#pragma unroll 5
+        for (int v = 0; v < V; ++v) {
+            const float z = a - b[v];
+            float t;
+            if (FAST) asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z));
+            else t = tanhf(z);
+            d[v] = t;
+        }
     }
 }
 
@@ -71,6 +91,7 @@ ctrgc_fwd_kernel(CtrgcP g, const T* __restrict__ x3, const float* __restrict__ x
     float* Ds = Qs + K * CT * V * VP;          // [R][V][DP]
     float* W4s = Ds + R * V * DP;              // [CT][R]
     float* st = W4s + CT * R;                  // [CT][2]
+    float* xs = st + CT * 2;                   // [2][R][V]  x1 / x2 of the current plane
     const int n = blockIdx.y, c0 = blockIdx.x * CT;
     const int nc = min(CT, g.Cout - c0);
     const float alpha = __ldg(alpha_p);
@@ -80,7 +101,7 @@ ctrgc_fwd_kernel(CtrgcP g, const T* __restrict__ x3, const float* __restrict__ x
 
     for (int i = 0; i < K; ++i) {
         __syncthreads();
-        build_D<V, DP>(Ds, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
+        build_D<V, DP, !std::is_same<T, float>::value>(Ds, xs, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
         for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
             W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
         __syncthreads();
@@ -159,6 +180,7 @@ ctrgc_bwd_kernel(CtrgcP g, Opnd go, const T* __restrict__ x3, const float* __res
     float* Ds = dQs + CT * V * DP;     // [R][V][DP]
     float* W4s = Ds + R * V * DP;      // [CT][R]
     float* red = W4s + CT * R;         // [64]
+    float* xs = red + 64;              // [2][R][V]  x1 / x2 of the current plane
     const int n = blockIdx.y, c0 = blockIdx.x * CT;
     const int nc = min(CT, g.Cout - c0);
     const float alpha = __ldg(alpha_p);
@@ -170,7 +192,7 @@ ctrgc_bwd_kernel(CtrgcP g, Opnd go, const T* __restrict__ x3, const float* __res
 
     for (int i = 0; i < K; ++i) {
         __syncthreads();
-        build_D<V, DP>(Ds, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
+        build_D<V, DP, !std::is_same<T, float>::value>(Ds, xs, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
         for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
             W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
         __syncthreads();
@@ -682,14 +704,14 @@ static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, c
     dim3 grid(cdiv(g.Cout, g.CT), g.N);
     if (V == 20) {
         constexpr int VP = VPad<20>::VP, DP = VPad<20>::DP;
-        const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 20 * VP + (size_t)g.R * 20 * DP + g.CT * g.R + g.CT * 2);
+        const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 20 * VP + (size_t)g.R * 20 * DP + g.CT * g.R + g.CT * 2 + 2 * g.R * 20);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
         static std::atomic<int> cur{48 * 1024};
         ensure_smem(ctrgc_fwd_kernel<T, 20>, cur, sm);
         ctrgc_fwd_kernel<T, 20><<<grid, 256, sm, st>>>(g, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)y, ssum, ssq);
     } else {
         constexpr int VP = VPad<25>::VP, DP = VPad<25>::DP;
-        const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 25 * VP + (size_t)g.R * 25 * DP + g.CT * g.R + g.CT * 2);
+        const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 25 * VP + (size_t)g.R * 25 * DP + g.CT * g.R + g.CT * 2 + 2 * g.R * 25);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
         static std::atomic<int> cur{48 * 1024};
         ensure_smem(ctrgc_fwd_kernel<T, 25>, cur, sm);
@@ -740,7 +762,7 @@ static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, co
     if (V == 20) {
         constexpr int VP = VPad<20>::VP, DP = VPad<20>::DP;
         const size_t sm = sizeof(float) * ((size_t)g.CT * 20 * VP + 2 * (size_t)g.CT * 20 * DP + (size_t)g.R * 20 * DP +
-                                           g.CT * g.R + 64);
+                                           g.CT * g.R + 64 + 2 * g.R * 20);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
         static std::atomic<int> cur{48 * 1024};
         ensure_smem(ctrgc_bwd_kernel<T, 20>, cur, sm);
@@ -749,7 +771,7 @@ static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, co
     } else {
         constexpr int VP = VPad<25>::VP, DP = VPad<25>::DP;
         const size_t sm = sizeof(float) * ((size_t)g.CT * 25 * VP + 2 * (size_t)g.CT * 25 * DP + (size_t)g.R * 25 * DP +
-                                           g.CT * g.R + 64);
+                                           g.CT * g.R + 64 + 2 * g.R * 25);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
         static std::atomic<int> cur{48 * 1024};
         ensure_smem(ctrgc_bwd_kernel<T, 25>, cur, sm);
