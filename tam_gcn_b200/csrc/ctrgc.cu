@@ -822,7 +822,13 @@ extern "C" int tamgcn_ctrgc_fwd(int dtype, const void* x3, int64_t x3_nstride, i
     CtrgcP g;
     g.N = N; g.Cout = Cout; g.T = T; g.K = K; g.R = R;
     g.CT = (V == 20) ? 16 : 8;
-    if (R > 16 && V == 25) g.CT = 4;
+    if (V == 25) {
+        // as many channels per CTA as fit ~200 KB of shared memory: every CTA of a sample rebuilds the tanh table, so the
+        // table cost scales with Cout / CT
+        const int s = dtype == TAMGCN_BF16 ? 4 : 4;          // the SIMT kernel keeps Q and D in fp32
+        while (g.CT > 1 && (size_t)s * ((size_t)K * g.CT * 25 * 28 + (size_t)R * 25 * 25 + g.CT * R + g.CT * 2 + 2 * R * 25) > 200 * 1024)
+            g.CT >>= 1;
+    }
     g.x3ns = x3_nstride; g.x12ns = x12_nstride; g.yns = y_nstride;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {     // tensor-core path (ctrgc_tc.cu); 0 = shape not covered, use the SIMT kernel
