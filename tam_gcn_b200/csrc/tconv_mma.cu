@@ -85,6 +85,47 @@ __device__ __forceinline__ void tm_load_tile(bf16* __restrict__ tile, int pitch,
             }
             *reinterpret_cast<uint2*>(tile + (size_t)ch * pitch + r * VP + v) = w;
         }
+    } else if (vec == 8) {
+        // Rows that are not 8-byte aligned (V = 25: 50-byte rows).  The rows row0 .. row0 + nrows - 1 of a channel are ONE
+        // contiguous element range in global memory, whatever V is: it is read in 16-byte pieces aligned in the GLOBAL
+        // address space (head / tail elements masked), and each element goes to its (row, v) slot of the padded tile with a
+        // 2-byte shared-memory store.  One division per 8 elements instead of two per element, 1/8 of the load instructions.
+        const int r_lo = row0 < 0 ? -row0 : 0, r_hi = (T - row0) < nrows ? (T - row0) : nrows;   // valid rows [r_lo, r_hi)
+        for (int idx = threadIdx.x; idx < CB * ((nrows * VP) >> 3); idx += TM_THREADS) {
+            const int ch = idx / ((nrows * VP) >> 3), k = idx - ch * ((nrows * VP) >> 3);
+            *reinterpret_cast<uint4*>(tile + (size_t)ch * pitch + 8 * k) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        if (r_hi > r_lo) {
+            const int g_lo = (row0 + r_lo) * V, g_hi = (row0 + r_hi) * V;           // element range inside a channel plane
+            const int nck = ((g_hi - g_lo) >> 3) + 2;                               // 16-byte pieces per channel (upper bound)
+            for (int idx = threadIdx.x; idx < CB * nck; idx += TM_THREADS) {
+                const int ch = idx / nck, k = idx - ch * nck;
+                const bf16* cp = pp + (long long)ch * TV;
+                const uintptr_t a0 = reinterpret_cast<uintptr_t>(cp + g_lo) & ~(uintptr_t)15;
+                const bf16* src = reinterpret_cast<const bf16*>(a0) + 8 * k;
+                int g = (int)(src - cp);                                            // element index of the piece's first element
+                if (g >= g_hi || g + 8 <= g_lo) continue;
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(src));
+                uint4 y = make_uint4(0u, 0u, 0u, 0u);
+                if (qq) y = __ldg(reinterpret_cast<const uint4*>(qq + (long long)ch * TV + g));   // same alignment required of q (host check)
+                const float a = coef[ch], b = coef[CB + ch], c = coef[2 * CB + ch];
+                const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+                int t = g >= 0 ? g / V : -1, v = g - t * V;                          // g >= g_lo - 7 >= -7
+                if (g < 0) { t = -1; v = g + V; }
+                bf16* dst = tile + (size_t)ch * pitch;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (g + j >= g_lo && g + j < g_hi) {
+                        float f = fmaf(a, (j & 1) ? tm_hi(xw[j >> 1]) : tm_lo(xw[j >> 1]), c);
+                        if (qq) f = fmaf(b, (j & 1) ? tm_hi(yw[j >> 1]) : tm_lo(yw[j >> 1]), f);
+                        if (o.relu) f = fmaxf(f, 0.f);
+                        dst[(t - row0) * VP + v] = __float2bfloat16_rn(f);
+                    }
+                    if (++v == V) { v = 0; ++t; }
+                }
+            }
+        }
     } else {
         const int per = nrows * VP, total = CB * per;
         for (int idx = threadIdx.x; idx < total; idx += TM_THREADS) {
@@ -351,7 +392,13 @@ static bool tm_al8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) 
 static int tm_vec(const Opnd& o, int V) {
     bool ok = (V % 4 == 0) && (o.pns % 4 == 0) && tm_al8(o.p);
     if (o.q) ok = ok && (o.qns % 4 == 0) && tm_al8(o.q);
-    return ok ? 4 : 1;
+    if (ok) return 4;
+    // flat 16-byte pieces (tm_load_tile, vec == 8): with a second tensor both must share the 16-byte phase of every
+    // channel plane, which holds when both bases are 16-byte aligned and the sample strides are multiples of 8 elements
+    static const int flat = [] { const char* e = getenv("TAMGCN_TCONV_FLAT"); return e ? atoi(e) : 1; }();
+    bool okf = flat && (o.pns % 8 == 0) && ((reinterpret_cast<uintptr_t>(o.p) & 15) == 0);
+    if (o.q) okf = okf && (o.qns % 8 == 0) && ((reinterpret_cast<uintptr_t>(o.q) & 15) == 0);
+    return okf ? 8 : 1;
 }
 static int tm_oddpitch(int elems) {                // multiple of 8 elements with an odd number of 16-byte pieces
     int p = (elems + 7) & ~7;

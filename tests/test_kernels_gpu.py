@@ -78,7 +78,7 @@ def _pad(k, d):
 
 
 @pytest.mark.parametrize('dt,geom,V,mode', [(dt, gm, V, md) for dt in DT for gm in CONV_GEOMS for V, md in
-                                            [(20, 'plain'), (25, 'affine_relu'), (20, 'two')]])
+                                            [(20, 'plain'), (25, 'affine_relu'), (20, 'two'), (25, 'plain')]])
 def test_conv_fwd(dt, geom, V, mode):
     _dev()
     from tam_gcn_b200 import ops
