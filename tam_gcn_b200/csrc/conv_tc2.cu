@@ -58,7 +58,7 @@ struct C2P {
     ConvP g;
     int IC, OC, Lin, Lout, KT, KTp, nchunk;
     int MT_total, n_oct, NT, NTp, nblk, tps, n_tiles;
-    int gran, upr, fast, vec, S, lag, tmem_cols, n_epi;
+    int gran, upr, fast, vec, S, lag, tmem_cols, n_epi, ra8;
     uint32_t x_bytes, q_bytes, stage_bytes, off_hdr, off_coef, off_stg;
     long long ons;
     int dbg;                 // TAMGCN_C2_DBG (profiling aid): 8 = print per-role blocked cycles of block 0
@@ -114,6 +114,32 @@ __device__ __forceinline__ uint32_t c2_xoff(uint32_t r, uint32_t pu) {
 }
 
 // input element offset (inside the sample plane of one channel) feeding output position pos through tap j; -1 = zero
+// 16 bytes starting `sft` (even, 0..14) bytes into the 32-byte pair (lo, hi): the realignment of a 2-byte aligned run of
+// 8 bf16 that was fetched as two 16-byte aligned words
+__device__ __forceinline__ uint4 c2_realign(const uint4& lo, const uint4& hi, uint32_t sft) {
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    const uint32_t ws = sft >> 2;
+    uint32_t o[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) o[i] = ws == 0 ? w[i] : (ws == 1 ? w[i + 1] : (ws == 2 ? w[i + 2] : w[i + 3]));
+    if (sft & 2u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __funnelshift_r(o[i], o[i + 1], 16);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// 8 consecutive bf16 at p (2-byte aligned): two aligned 16-byte loads + realignment.  The second word is only touched
+// when the run extends into it, so no byte outside the 16-byte granules that hold valid data is read.
+__device__ __forceinline__ uint4 c2_ld8_unaligned(const bf16* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t sft = (uint32_t)(a & 15);
+    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint4 lo = __ldg(q);
+    if (sft == 0) return lo;
+    const uint4 hi = __ldg(q + 1);
+    return c2_realign(lo, hi, sft);
+}
+
 template <int MODE>
 __device__ __forceinline__ int c2_in_off(const ConvP& g, int pos, int j) {
     const int tq = pos / g.V, v = pos - tq * g.V;
@@ -461,8 +487,64 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                         if (lag == 2) c2_wait_group<2>(); else if (lag == 1) c2_wait_group<1>(); else c2_wait_group<0>();
                         retire(lag, stg);
                     }
+                } else if (p.ra8) {
+                    // stride-1 taps whose V-row shift is not 8-byte aligned (V = 25: 50-byte rows): 8 consecutive positions of
+                    // a K row are still 8 consecutive source elements (offset pos + shift * V), only 2-byte aligned.  Fetched
+                    // as aligned 16-byte words and realigned in registers, transformed, stored as one 16-byte chunk — instead
+                    // of eight 2-byte loads and stores.  Units cut by the sample boundary take the element path below.
+                    const int upr8 = NT >> 3;
+                    const unsigned total = (unsigned)(rows * upr8);
+#pragma unroll 1
+                    for (unsigned idx = pt; idx < total; idx += C2_PR_T) {
+                        const int r = (int)(idx / (unsigned)upr8), pu = (int)(idx - (unsigned)r * upr8) * 8;
+                        const int kf = kbase + r, pos = pos0 + pu;
+                        const int j = p.fast ? 0 : kf / IC, ic = kf - j * IC;
+                        const int off = pos + (MODE == 0 ? j * g.d - g.p : g.p - j * g.d) * g.V;
+                        const uint32_t dst = sx + c2_xoff((uint32_t)r, (uint32_t)pu);
+                        if (kf >= p.KT || pos >= Lout || off + 8 <= 0 || off >= Lin) {
+                            st_shared_v4(dst, 0u, 0u, 0u, 0u);
+                            continue;
+                        }
+                        const float ca = coef[ic], cb = coef[IC + ic], cc = coef[2 * IC + ic];
+                        uint32_t w[4];
+                        if (off >= 0 && off + 8 <= Lin && pos + 8 <= Lout) {
+                            const long long e = (long long)ic * Lin + off;
+                            const uint4 x = c2_ld8_unaligned(pn + e);
+                            uint4 y = make_uint4(0u, 0u, 0u, 0u);
+                            if (has_q) y = c2_ld8_unaligned(qn + e);
+                            const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                float lo = fmaf(ca, __uint_as_float(xw[h] << 16), cc), hi = fmaf(ca, __uint_as_float(xw[h] & 0xffff0000u), cc);
+                                if (has_q) {
+                                    lo = fmaf(cb, __uint_as_float(yw[h] << 16), lo);
+                                    hi = fmaf(cb, __uint_as_float(yw[h] & 0xffff0000u), hi);
+                                }
+                                if (xo.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                                w[h] = pack_bf16(lo, hi);
+                            }
+                        } else {
+                            float v8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float val = 0.f;
+                                if (off + i >= 0 && off + i < Lin && pos + i < Lout) {
+                                    const long long e = (long long)ic * Lin + off + i;
+                                    val = fmaf(ca, ldf<bf16>(pn + e), cc);
+                                    if (has_q) val = fmaf(cb, ldf<bf16>(qn + e), val);
+                                    if (xo.relu) val = fmaxf(val, 0.f);
+                                }
+                                v8[i] = val;
+                            }
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) w[h] = pack_bf16(v8[2 * h], v8[2 * h + 1]);
+                        }
+                        st_shared_v4(dst, w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&hdr->full[stg]);
                 } else {
-                    // element-granular path (odd plane sizes, V = 25 taps): 2-byte loads and stores
+                    // element-granular path (odd plane sizes, strided V = 25 taps): 2-byte loads and stores
                     const int total = rows * NT;
 #pragma unroll 1
                     for (int idx = pt; idx < total; idx += C2_PR_T) {
@@ -630,6 +712,8 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
     p.NTp = (NT + 31) & ~31;
     p.nblk = (NT + 63) / 64;
     p.upr = p.gran >= 4 ? NT / p.gran : NT;
+    static const int ra8_env = [] { const char* e = getenv("TAMGCN_C2_RA8"); return e ? atoi(e) : 1; }();
+    p.ra8 = (ra8_env && p.gran == 1 && g.s == 1 && NT % 8 == 0) ? 1 : 0;
     if (p.gran >= 4 && NT % p.gran != 0) return 0;
     const long long tiles = (long long)g.N * p.tps;
     if (tiles > 0x7fffffffLL) return 0;
