@@ -114,32 +114,6 @@ __device__ __forceinline__ uint32_t c2_xoff(uint32_t r, uint32_t pu) {
 }
 
 // input element offset (inside the sample plane of one channel) feeding output position pos through tap j; -1 = zero
-// 16 bytes starting `sft` (even, 0..14) bytes into the 32-byte pair (lo, hi): the realignment of a 2-byte aligned run of
-// 8 bf16 that was fetched as two 16-byte aligned words
-__device__ __forceinline__ uint4 c2_realign(const uint4& lo, const uint4& hi, uint32_t sft) {
-    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    const uint32_t ws = sft >> 2;
-    uint32_t o[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) o[i] = ws == 0 ? w[i] : (ws == 1 ? w[i + 1] : (ws == 2 ? w[i + 2] : w[i + 3]));
-    if (sft & 2u) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = __funnelshift_r(o[i], o[i + 1], 16);
-    }
-    return make_uint4(o[0], o[1], o[2], o[3]);
-}
-// 8 consecutive bf16 at p (2-byte aligned): two aligned 16-byte loads + realignment.  The second word is only touched
-// when the run extends into it, so no byte outside the 16-byte granules that hold valid data is read.
-__device__ __forceinline__ uint4 c2_ld8_unaligned(const bf16* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t sft = (uint32_t)(a & 15);
-    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-    const uint4 lo = __ldg(q);
-    if (sft == 0) return lo;
-    const uint4 hi = __ldg(q + 1);
-    return c2_realign(lo, hi, sft);
-}
-
 template <int MODE>
 __device__ __forceinline__ int c2_in_off(const ConvP& g, int pos, int j) {
     const int tq = pos / g.V, v = pos - tq * g.V;
@@ -509,9 +483,9 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                         uint32_t w[4];
                         if (off >= 0 && off + 8 <= Lin && pos + 8 <= Lout) {
                             const long long e = (long long)ic * Lin + off;
-                            const uint4 x = c2_ld8_unaligned(pn + e);
+                            const uint4 x = tc_ld8_unaligned(pn + e);
                             uint4 y = make_uint4(0u, 0u, 0u, 0u);
-                            if (has_q) y = c2_ld8_unaligned(qn + e);
+                            if (has_q) y = tc_ld8_unaligned(qn + e);
                             const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
                             for (int h = 0; h < 4; ++h) {

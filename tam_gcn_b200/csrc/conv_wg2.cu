@@ -25,7 +25,7 @@ struct ConvP {
 struct W2P {
     ConvP g;
     int Lin, Lout, NT, NTp, nchunk, units;
-    int gran_a, gran_b, fast, S, lag, tmem_cols, has_bias, flat;
+    int gran_a, gran_b, fast, S, lag, tmem_cols, has_bias, flat, rab;
     uint32_t a_bytes, aq_bytes, b_bytes, bq_bytes, stage_bytes, off_hdr, off_coef;
 };
 
@@ -164,7 +164,7 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
                     else w2_xform<4>(ud, ud + p.a_bytes, a_q, coefA[r], coefA[128 + r], coefA[256 + r], dyo.relu);
                 }
             }
-            if (b_lazy) {
+            if (b_lazy && !p.rab) {
                 const int per = nci << shb, tot = k * per;
 #pragma unroll 1
                 for (int idx = tid; idx < tot; idx += W2_PR_T) {
@@ -201,7 +201,54 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
                     else { w2_cp8(dst, pn + ep, ok ? 8u : 0u); if (a_q) w2_cp8(dst + p.a_bytes, qn + eq, ok ? 8u : 0u); }
                 }
             }
-            {   // B_j: X rows shifted by tap j
+            if (p.rab) {
+                // stride-1 taps whose V-row shift is only 2-byte aligned (V = 25): no cp.async granularity fits.  8 consecutive
+                // positions of a row are 8 consecutive source elements: aligned 16-byte words, realigned in registers,
+                // transformed here (retire() skips B), stored as one 16-byte chunk.
+                const bf16* pn = bp + (long long)n * xo.pns + (long long)ci0 * Lin;
+                const bf16* qn = b_q ? bq + (long long)n * xo.qns + (long long)ci0 * Lin : nullptr;
+                const int per = nci << 3, tot = k * per;
+#pragma unroll 1
+                for (int idx = tid; idx < tot; idx += W2_PR_T) {
+                    const int j = idx / per, i2 = idx - j * per;
+                    const int r = i2 >> 3, pu = (i2 & 7) * 8;
+                    const int pos = pos0 + pu, off = pos + (j * g.d - g.p) * g.V;
+                    const uint32_t dst = sB + (uint32_t)(j * NTp) * 128u + w2_off((uint32_t)r, (uint32_t)pu);
+                    if (pos >= Lout || off + 8 <= 0 || off >= Lin) { st_shared_v4(dst, 0u, 0u, 0u, 0u); continue; }
+                    const float ca = coefB[r], cb = coefB[NT + r], cc = coefB[2 * NT + r];
+                    uint32_t w[4];
+                    if (off >= 0 && off + 8 <= Lin && pos + 8 <= Lout) {
+                        const long long e = (long long)r * Lin + off;
+                        const uint4 x = tc_ld8_unaligned(pn + e);
+                        uint4 y = make_uint4(0u, 0u, 0u, 0u);
+                        if (b_q) y = tc_ld8_unaligned(qn + e);
+                        const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            float lo = fmaf(ca, w2_lo(xw[h]), cc), hi = fmaf(ca, w2_hi(xw[h]), cc);
+                            if (b_q) { lo = fmaf(cb, w2_lo(yw[h]), lo); hi = fmaf(cb, w2_hi(yw[h]), hi); }
+                            if (xo.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                            w[h] = pack_bf16(lo, hi);
+                        }
+                    } else {
+                        float v8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float val = 0.f;
+                            if (off + i >= 0 && off + i < Lin && pos + i < Lout) {
+                                const long long e = (long long)r * Lin + off + i;
+                                val = fmaf(ca, __bfloat162float(pn[e]), cc);
+                                if (b_q) val = fmaf(cb, __bfloat162float(qn[e]), val);
+                                if (xo.relu) val = fmaxf(val, 0.f);
+                            }
+                            v8[i] = val;
+                        }
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) w[h] = pack_bf16(v8[2 * h], v8[2 * h + 1]);
+                    }
+                    st_shared_v4(dst, w[0], w[1], w[2], w[3]);
+                }
+            } else {   // B_j: X rows shifted by tap j
                 const bf16* pn = bp + (long long)n * xo.pns + (long long)ci0 * Lin;
                 const bf16* qn = b_q ? bq + (long long)n * xo.qns + (long long)ci0 * Lin : nullptr;
                 const int per = nci << shb, tot = k * per;
@@ -325,6 +372,8 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     p.gran_a = (al(dy.p, dy.pns, p.Lout, 8) && al(dy.q, dy.qns, p.Lout, 8)) ? 8 : ((al(dy.p, dy.pns, p.Lout, 4) && al(dy.q, dy.qns, p.Lout, 4)) ? 4 : 0);
     auto okb = [&](int gr) { return al(x.p, x.pns, p.Lin, gr) && al(x.q, x.qns, p.Lin, gr) && (p.fast ? (p.Lout % gr == 0) : (g.V % gr == 0)); };
     p.gran_b = okb(8) ? 8 : (okb(4) ? 4 : 0);
+    static const int rab_env = [] { const char* e = getenv("TAMGCN_W2_RAB"); return e ? atoi(e) : 1; }();
+    if (p.gran_b == 0 && rab_env && !p.fast && g.s == 1) { p.rab = 1; p.gran_b = 8; }   // register path for the B operand
     if (p.gran_a == 0 || p.gran_b == 0) return 0;
     // ci tile: k column groups of NTp (>= NT + 1 for the ones row) must fit 512 TMEM columns
     int NT = (g.Cin + 15) & ~15;

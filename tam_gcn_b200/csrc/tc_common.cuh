@@ -185,6 +185,32 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 16 bytes starting `sft` (even, 0..14) bytes into the 32-byte pair (lo, hi): the realignment of a 2-byte aligned run of
+// 8 bf16 that was fetched as two 16-byte aligned words
+__device__ __forceinline__ uint4 tc_realign16(const uint4& lo, const uint4& hi, uint32_t sft) {
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    const uint32_t ws = sft >> 2;
+    uint32_t o[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) o[i] = ws == 0 ? w[i] : (ws == 1 ? w[i + 1] : (ws == 2 ? w[i + 2] : w[i + 3]));
+    if (sft & 2u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __funnelshift_r(o[i], o[i + 1], 16);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// 8 consecutive bf16 at p (2-byte aligned): two aligned 16-byte loads + realignment.  The second word is only touched
+// when the run extends into it, so no byte outside the 16-byte granules that hold valid data is read.
+__device__ __forceinline__ uint4 tc_ld8_unaligned(const bf16* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t sft = (uint32_t)(a & 15);
+    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint4 lo = __ldg(q);
+    if (sft == 0) return lo;
+    const uint4 hi = __ldg(q + 1);
+    return tc_realign16(lo, hi, sft);
+}
+
 // Per-column sum of a 32 (lanes = rows) x 32 (registers = columns) tile: after the call lane L holds the sum of
 // column L over the 32 lanes.  31 shuffles instead of 160.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
