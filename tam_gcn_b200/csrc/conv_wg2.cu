@@ -25,7 +25,7 @@ struct ConvP {
 struct W2P {
     ConvP g;
     int Lin, Lout, NT, NTp, nchunk, units;
-    int gran_a, gran_b, fast, S, lag, tmem_cols, has_bias, flat, rab;
+    int gran_a, gran_b, fast, S, lag, tmem_cols, has_bias, flat, rab, raa;
     uint32_t a_bytes, aq_bytes, b_bytes, bq_bytes, stage_bytes, off_hdr, off_coef;
 };
 
@@ -153,7 +153,7 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
             int n, pos0;
             chunk_origin(u, n, pos0);
             const uint32_t sA = s0 + (uint32_t)sp * p.stage_bytes, sB = sA + p.a_bytes + p.aq_bytes;
-            if (a_lazy) {
+            if (a_lazy && !p.raa) {
                 const int tot = nco << sha;
 #pragma unroll 1
                 for (int idx = tid; idx < tot; idx += W2_PR_T) {
@@ -185,7 +185,52 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
             chunk_origin(u, n, pos0);
             if (!mbar_wait(&hdr->empty[stg], (uint32_t)(ph ^ 1))) hdr->error = 1;
             const uint32_t sA = s0 + (uint32_t)stg * p.stage_bytes, sB = sA + p.a_bytes + p.aq_bytes;
-            {   // A: dY rows
+            if (p.raa) {
+                // dY rows that are not 8-byte aligned (odd T*V: channel planes start on 2- or 4-byte boundaries): same register
+                // path as the tap-shifted operand below, shift 0
+                const bf16* pn = ap + (long long)n * dyo.pns + (long long)co0 * Lout;
+                const bf16* qn = a_q ? aq + (long long)n * dyo.qns + (long long)co0 * Lout : nullptr;
+                const int tot = nco << 3;
+#pragma unroll 1
+                for (int idx = tid; idx < tot; idx += W2_PR_T) {
+                    const int r = idx >> 3, pu = (idx & 7) * 8;
+                    const int pos = pos0 + pu;
+                    const uint32_t dst = sA + w2_off((uint32_t)r, (uint32_t)pu);
+                    if (pos >= Lout) { st_shared_v4(dst, 0u, 0u, 0u, 0u); continue; }
+                    const float ca = coefA[r], cb = coefA[128 + r], cc = coefA[256 + r];
+                    uint32_t w[4];
+                    if (pos + 8 <= Lout) {
+                        const long long e = (long long)r * Lout + pos;
+                        const uint4 x = tc_ld8_unaligned(pn + e);
+                        uint4 y = make_uint4(0u, 0u, 0u, 0u);
+                        if (a_q) y = tc_ld8_unaligned(qn + e);
+                        const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            float lo = fmaf(ca, w2_lo(xw[h]), cc), hi = fmaf(ca, w2_hi(xw[h]), cc);
+                            if (a_q) { lo = fmaf(cb, w2_lo(yw[h]), lo); hi = fmaf(cb, w2_hi(yw[h]), hi); }
+                            if (dyo.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                            w[h] = pack_bf16(lo, hi);
+                        }
+                    } else {
+                        float v8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float val = 0.f;
+                            if (pos + i < Lout) {
+                                const long long e = (long long)r * Lout + pos + i;
+                                val = fmaf(ca, __bfloat162float(pn[e]), cc);
+                                if (a_q) val = fmaf(cb, __bfloat162float(qn[e]), val);
+                                if (dyo.relu) val = fmaxf(val, 0.f);
+                            }
+                            v8[i] = val;
+                        }
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) w[h] = pack_bf16(v8[2 * h], v8[2 * h + 1]);
+                    }
+                    st_shared_v4(dst, w[0], w[1], w[2], w[3]);
+                }
+            } else {   // A: dY rows
                 const bf16* pn = ap + (long long)n * dyo.pns + (long long)co0 * Lout + pos0;
                 const bf16* qn = a_q ? aq + (long long)n * dyo.qns + (long long)co0 * Lout + pos0 : nullptr;
                 const int tot = nco << sha;
@@ -373,7 +418,8 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     auto okb = [&](int gr) { return al(x.p, x.pns, p.Lin, gr) && al(x.q, x.qns, p.Lin, gr) && (p.fast ? (p.Lout % gr == 0) : (g.V % gr == 0)); };
     p.gran_b = okb(8) ? 8 : (okb(4) ? 4 : 0);
     static const int rab_env = [] { const char* e = getenv("TAMGCN_W2_RAB"); return e ? atoi(e) : 1; }();
-    if (p.gran_b == 0 && rab_env && !p.fast && g.s == 1) { p.rab = 1; p.gran_b = 8; }   // register path for the B operand
+    if (p.gran_b == 0 && rab_env && g.s == 1) { p.rab = 1; p.gran_b = 8; }               // register path for the B operand
+    if (p.gran_a == 0 && rab_env) { p.raa = 1; p.gran_a = 8; }                             // ... and for the A operand
     if (p.gran_a == 0 || p.gran_b == 0) return 0;
     // ci tile: k column groups of NTp (>= NT + 1 for the ones row) must fit 512 TMEM columns
     int NT = (g.Cin + 15) & ~15;
@@ -384,7 +430,7 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     p.tmem_cols = (int)tmem_cols_pow2((uint32_t)(g.k * p.NTp));
     p.nchunk = (p.Lout + 63) / 64;
     static const int flat_env = [] { const char* e = getenv("TAMGCN_W2_FLAT"); return e ? atoi(e) : 1; }();
-    p.flat = (flat_env && p.fast && p.Lout >= 64 && p.Lout % 64 != 0) ? 1 : 0;
+    p.flat = (flat_env && p.fast && !p.rab && !p.raa && p.Lout >= 64 && p.Lout % 64 != 0) ? 1 : 0;
     const long long units = p.flat ? ((long long)g.N * p.Lout + 63) / 64 : (long long)g.N * p.nchunk;
     if (units > 0x7fffffffLL) return 0;
     p.units = (int)units;
