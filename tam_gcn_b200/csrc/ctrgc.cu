@@ -102,16 +102,47 @@ ctrgc_fwd_kernel(CtrgcP g, const T* __restrict__ x3, const float* __restrict__ x
     for (int i = 0; i < K; ++i) {
         __syncthreads();
         build_D<V, DP, !std::is_same<T, float>::value>(Ds, xs, x1 + (long long)n * g.x12ns + i * R * V, x2 + (long long)n * g.x12ns + i * R * V, R);
-        for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
-            W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < nc * V * V; idx += blockDim.x) {
-            const int c = idx / (V * V), rem = idx - c * V * V, u = rem / V, v = rem - u * V;
-            float acc = __ldg(b4 + i * g.Cout + c0 + c);
-            const float* d = Ds + u * DP + v;
-            const float* w = W4s + c * R;
-            for (int r = 0; r < R; ++r) acc = fmaf(w[r], d[r * V * DP], acc);
-            Qs[((i * CT + c) * V + u) * VP + v] = fmaf(alpha, acc, __ldg(PA + (i * V + u) * V + v));
+        if ((CT & 3) == 0 && (R & 3) == 0) {
+            // W4 of the CTA's channels transposed to [r][CT]: a thread owns one (u, v) and FOUR channels, so every tanh value
+            // it reads feeds four FMAs and the four weights arrive as one 16-byte shared-memory load (the scalar loop below
+            // spent two loads per FMA and was 55 % of the kernel's instructions at R = 32)
+            for (int idx = threadIdx.x; idx < CT * R; idx += blockDim.x) {
+                const int r = idx / CT, c = idx - r * CT;
+                W4s[idx] = c < nc ? __ldg(W4 + ((long long)i * g.Cout + c0 + c) * R + r) : 0.f;
+            }
+            __syncthreads();
+            const int ncq = (nc + 3) >> 2;
+            for (int idx = threadIdx.x; idx < ncq * V * V; idx += blockDim.x) {
+                const int cq = idx / (V * V), rem = idx - cq * V * V, u = rem / V, v = rem - u * V;
+                float acc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] = (4 * cq + k < nc) ? __ldg(b4 + i * g.Cout + c0 + 4 * cq + k) : 0.f;
+                const float* d = Ds + u * DP + v;
+                const float* w = W4s + 4 * cq;
+#pragma unroll 4
+                for (int r = 0; r < R; ++r) {
+                    const float dv = d[r * V * DP];
+                    const float4 wv = *reinterpret_cast<const float4*>(w + r * CT);
+                    acc[0] = fmaf(wv.x, dv, acc[0]); acc[1] = fmaf(wv.y, dv, acc[1]);
+                    acc[2] = fmaf(wv.z, dv, acc[2]); acc[3] = fmaf(wv.w, dv, acc[3]);
+                }
+                const float pa = __ldg(PA + (i * V + u) * V + v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (4 * cq + k < nc) Qs[((i * CT + 4 * cq + k) * V + u) * VP + v] = fmaf(alpha, acc[k], pa);
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < nc * R; idx += blockDim.x)
+                W4s[idx] = __ldg(W4 + ((long long)i * g.Cout + c0) * R + idx);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < nc * V * V; idx += blockDim.x) {
+                const int c = idx / (V * V), rem = idx - c * V * V, u = rem / V, v = rem - u * V;
+                float acc = __ldg(b4 + i * g.Cout + c0 + c);
+                const float* d = Ds + u * DP + v;
+                const float* w = W4s + c * R;
+                for (int r = 0; r < R; ++r) acc = fmaf(w[r], d[r * V * DP], acc);
+                Qs[((i * CT + c) * V + u) * VP + v] = fmaf(alpha, acc, __ldg(PA + (i * V + u) * V + v));
+            }
         }
     }
     __syncthreads();
