@@ -55,6 +55,7 @@ struct CtcP {
     int w4t_floats;
     int lg2G;
     int dbg;                         // TAMGCN_CTC_DBG bit mask (profiling aid): 1 skip x3 copies, 2 skip Q math, 4 skip copy-out
+    int ra25;                        // V = 25: rows fetched as aligned 16-byte words and realigned in registers
 };
 
 // (sample, channel group, time chunk) of consecutive tiles without integer divisions
@@ -516,6 +517,34 @@ ctrgc_fwd_tc_kernel(CtcP p, const bf16* __restrict__ x3, const float* __restrict
                             cp_async8(sa + row * 128u + (((byte >> 4) ^ (row & 7u)) << 4) + (byte & 15u), src);
                         }
                     }
+                } else if (p.ra25) {
+                    // V = 25: a row is 50 bytes on a 2-byte boundary.  Its first 24 elements are fetched as aligned 16-byte
+                    // words and realigned in registers into the three 16-byte chunks of the operand row, element 24 follows
+                    // alone (the rest of its chunk is K padding = 0): 4 stores per row instead of 25.
+                    const unsigned rows = (unsigned)(Gv * K * TRv);
+                    const unsigned rmagic = 0xFFFFFFFFu / (unsigned)TRv + 1u;
+#pragma unroll 2
+                    for (unsigned idx = lt; idx < rows; idx += LGT) {
+                        const unsigned gi = __umulhi(idx, rmagic), t = idx - gi * (unsigned)TRv;
+                        const unsigned g = (gi * p.kmagic) >> 16, i = gi - g * K;
+                        const bf16* src = xn + ((long long)(i * p.Cout + cs + g) * p.T + t0 + t) * 25;
+                        const unsigned row = g * TR + t, c0 = (i & 1u) * 4u, sw = row & 7u;
+                        const uint32_t rb = sa + (i >> 1) * 16384u + row * 128u;
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+                        const uint32_t sft = (uint32_t)(a & 15);
+                        const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                        const uint4 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+                        uint4 k0 = w0, k1 = w1, k2 = w2;
+                        if (sft) {
+                            const uint4 w3 = __ldg(q + 3);
+                            k0 = tc_realign16(w0, w1, sft); k1 = tc_realign16(w1, w2, sft); k2 = tc_realign16(w2, w3, sft);
+                        }
+                        const uint32_t e24 = __ldg(reinterpret_cast<const unsigned short*>(src + 24));
+                        st_shared_v4(rb + (((c0 + 0u) ^ sw) << 4), k0.x, k0.y, k0.z, k0.w);
+                        st_shared_v4(rb + (((c0 + 1u) ^ sw) << 4), k1.x, k1.y, k1.z, k1.w);
+                        st_shared_v4(rb + (((c0 + 2u) ^ sw) << 4), k2.x, k2.y, k2.z, k2.w);
+                        st_shared_v4(rb + (((c0 + 3u) ^ sw) << 4), e24, 0u, 0u, 0u);
+                    }
                 } else {
                     const int av = p.av;
                     const unsigned nvec = (unsigned)(TRv * 25 / av), total = (unsigned)(Gv * K) * nvec;
@@ -728,6 +757,7 @@ int ctrgc_fwd_tc(const void* x3, long long x3ns, int N, int Cout, int T, int V, 
     p.Nmma = (p.Nmma + 15) & ~15;
     p.kmagic = 65536u / (unsigned)K + 1u;
     { const char* e = getenv("TAMGCN_CTC_DBG"); p.dbg = e ? atoi(e) : 0; }
+    { const char* e = getenv("TAMGCN_CTC_RA25"); p.ra25 = (V == 25 && !(e && e[0] == '0')) ? 1 : 0; }
     p.a_bytes = (uint32_t)p.NKB * 16384u;
     p.b_blk_bytes = (uint32_t)p.Nmma * 128u;
     p.b_bytes = (uint32_t)p.NKB * p.b_blk_bytes;
