@@ -185,6 +185,44 @@ int tamgcn_graph_agg_bwd(int dtype, int N, int K, int C, int T, int V, const tam
                          int64_t y_nstride, const float* A, void* dy, int64_t dy_nstride, float* dA,
                          tamgcn_stream stream);
 
+/* ---- network ends and optimiser -------------------------------------------------- */
+/* Model.forward prologue, models/ctrgcn.py:328-332 (fold_m = 0) and models/stgcn.py:174-181 (fold_m = 1):
+ *   x.permute(0,4,3,1,2).view(N, M*V*C, T) -> nn.BatchNorm1d -> view/permute -> (N*M, C, T, V) in `dtype`.
+ * x is fp32 with arbitrary element strides x_strides[5] for the (n, c, t, v, m) axes (so both the 5-D input and the
+ * (N, T, V*C) input of models/ctrgcn.py:325-327 are read in place).  BatchNorm channel = (m*V + v)*C + c, or v*C + c
+ * with the persons folded into the batch (fold_m).  Train: batch statistics (fp64 sums inside the CTA), running-stat
+ * update with `momentum`, *nbt += 1; eval: running statistics.  save_mean / save_invstd (per channel, may be NULL)
+ * are what tamgcn_data_bn_bwd needs. */
+int tamgcn_data_bn_fwd(int dtype, const float* x, const int64_t* x_strides, int N, int C, int T, int V, int M, int fold_m,
+                       const float* gamma, const float* beta, float* rmean, float* rvar, int64_t* nbt, float momentum,
+                       float eps, int train, void* out, float* save_mean, float* save_invstd, tamgcn_stream stream);
+/* g: cotangent of the (N*M, C, T, V) output.  dgamma / dbeta "+=" (NULL to skip); dx: contiguous fp32 (N, C, T, V, M)
+ * or NULL when the input needs no gradient. */
+int tamgcn_data_bn_bwd(int dtype, const void* g, const float* x, const int64_t* x_strides, int N, int C, int T, int V,
+                       int M, int fold_m, const float* gamma, const float* mean, const float* invstd, int train,
+                       float* dgamma, float* dbeta, float* dx, tamgcn_stream stream);
+/* Model.forward head, models/ctrgcn.py:343-348 / models/stgcn.py:187-195: pooled[n,c] = mean over persons and (T*V) of
+ * x[(n*M+m), c, :]; logits = pooled W^T + b (W (K,C), b (K) or NULL; W == NULL: pooling only).  pooled (N,C), logits (N,K) fp32. */
+int tamgcn_pool_fc_fwd(int dtype, const void* x, int N, int M, int C, int TV, int K, const float* W, const float* b,
+                       float* pooled, float* logits, tamgcn_stream stream);
+/* g[(n*M+m), c, :] = (sum_k dlogits[n,k] W[k,c]) / (M*TV)  (NULL to skip);  dW[k,c] += dlogits[n,k]*pooled[n,c];
+ * db[k] += dlogits[n,k]  (NULL to skip).  W == NULL (pooling only, K == C): dlogits is the cotangent of pooled. */
+int tamgcn_pool_fc_bwd(int dtype, const float* dlogits, const float* pooled, const float* W, int N, int M, int C, int TV,
+                       int K, void* g, float* dW, float* db, tamgcn_stream stream);
+/* nn.CrossEntropyLoss (mean over the samples whose label is in [0,K); other labels, e.g. -100, are ignored),
+ * processor/recognition_rgb.py:19,61.  loss: one float; dlogits (N,K) = d loss / d logits (NULL to skip). */
+int tamgcn_softmax_ce_fwd(const float* logits, const int64_t* labels, int N, int K, float* loss, float* dlogits,
+                          tamgcn_stream stream);
+/* dlogits = dl_saved * gloss[0]  (chain rule through the scalar loss) */
+int tamgcn_softmax_ce_bwd(const float* dl_saved, const float* gloss, int N, int K, float* dlogits, tamgcn_stream stream);
+/* torch.optim.SGD(momentum, nesterov, weight_decay; dampening 0) over flat fp32 buffers of n elements
+ * (processor/recognition_rgb.py:21-28):  g = grads*grad_scale + wd*p;  m = momentum*m + g;
+ * p -= lr * (nesterov ? g + momentum*m : m).  `lr` is a DEVICE pointer so a captured CUDA graph follows
+ * adjust_learning_rate (processor/recognition_rgb.py:43-46).  A zero-initialised momentum buffer reproduces torch's
+ * first step (buf = g).  Buffers must be 16-byte aligned. */
+int tamgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, const float* lr, float momentum,
+                    float weight_decay, int nesterov, float grad_scale, tamgcn_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

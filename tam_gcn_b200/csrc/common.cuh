@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/tamgcn.h"
 
@@ -20,6 +21,27 @@ typedef __nv_bfloat16 bf16;
 int set_error(const char* fmt, ...);          // returns -1
 void count_launch(int n = 1);
 int check_launch(const char* what);           // cudaGetLastError -> 0 / -2
+
+// ---- per-device launch state ------------------------------------------------------------------
+// The opt-in dynamic shared-memory limit (cudaFuncSetAttribute) and the SM count belong to a DEVICE, while this
+// library lives once per PROCESS: under nn.DataParallel (processor/io.py:85-87) one process drives several devices
+// from several threads, so both are cached per device ordinal, and raising a limit is serialised by a mutex.
+constexpr int TG_MAX_DEVICES = 64;
+int current_device();                          // cudaGetDevice, clamped to [0, TG_MAX_DEVICES)
+int num_sms();                                 // SM count of the current device (cached per device)
+struct SmemLimit {                             // one per kernel instantiation (function-local static)
+    std::atomic<int> cur[TG_MAX_DEVICES];
+    SmemLimit() { for (int i = 0; i < TG_MAX_DEVICES; ++i) cur[i].store(48 * 1024, std::memory_order_relaxed); }
+};
+void raise_smem_limit(const void* kernel, SmemLimit& lim, int dev, size_t bytes);   // slow path, mutex inside
+// raise the dynamic shared-memory limit of `kernel` on the current device only when a larger size than ever before
+// is needed there (warm-up calls do it; replays / CUDA-graph captures then issue no attribute call)
+template <typename K>
+static inline void ensure_smem(K kernel, SmemLimit& lim, size_t bytes) {
+    if (bytes <= 48 * 1024) return;
+    const int dev = current_device();
+    if ((int)bytes > lim.cur[dev].load(std::memory_order_acquire)) raise_smem_limit((const void*)kernel, lim, dev, bytes);
+}
 
 #define TG_REQUIRE(cond, ...)                       \
     do {                                            \

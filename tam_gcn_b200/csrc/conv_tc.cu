@@ -186,11 +186,8 @@ int conv_wgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, floa
     if (S > units) S = units;
     if (S < 1) S = 1;
     if (S > 65535) S = 65535;
-    static int cur = 48 * 1024;
-    if ((int)sm > cur) {
-        cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cur = (int)sm;
-    }
+    static SmemLimit lim;
+    ensure_smem(conv_wgrad_tc_kernel, lim, sm);
     dim3 grid(gx, gy, (unsigned)S);
     conv_wgrad_tc_kernel<<<grid, TC_THREADS, sm, st>>>(p, dy, x, dW, dbias, NT, NTp, nchunk, cols);
     count_launch();

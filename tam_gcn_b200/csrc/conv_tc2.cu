@@ -600,16 +600,7 @@ static bool c2_disabled() {
     }
     return v == 1;
 }
-static int c2_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int c2_num_sms() { return num_sms(); }
 static int oc_pad128(int OC) { return (OC + 127) & ~127; }
 
 size_t conv_pack_bytes(int Cout, int Cin, int k, int dgrad) {
@@ -736,11 +727,8 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
     }
 #define C2_LAUNCH(PL, EX)                                                                                              \
     do {                                                                                                               \
-        static int cur = 48 * 1024;                                                                                    \
-        if ((int)sm > cur) {                                                                                           \
-            cudaFuncSetAttribute(conv_tc2_kernel<MODE, PL, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-            cur = (int)sm;                                                                                             \
-        }                                                                                                              \
+        static SmemLimit lim;                                                                                          \
+        ensure_smem(conv_tc2_kernel<MODE, PL, EX>, lim, sm);                                                           \
         conv_tc2_kernel<MODE, PL, EX><<<grid, EX ? C2_THREADS_SMALL : C2_THREADS_BIG, sm, st>>>(p, xo, (const uint8_t*)wpack, (bf16*)out, ep); \
     } while (0)
     if (MODE == 0 || !extra) { if (plain) C2_LAUNCH(1, 0); else C2_LAUNCH(0, 0); }

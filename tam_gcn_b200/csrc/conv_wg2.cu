@@ -391,16 +391,7 @@ static bool w2_disabled() {
     }
     return v == 1;
 }
-static int w2_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int w2_num_sms() { return num_sms(); }
 
 // return 1 if handled, 0 if the caller should use another kernel, <0 on error
 int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st) {
@@ -465,11 +456,8 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     if (Z < 1) Z = 1;
     if (Z > units) Z = units;
     if (Z > 65535) Z = 65535;
-    static int cur = 48 * 1024;
-    if ((int)sm > cur) {
-        cudaFuncSetAttribute(conv_wg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cur = (int)sm;
-    }
+    static SmemLimit lim;
+    ensure_smem(conv_wg2_kernel, lim, sm);
     dim3 grid(gx, gy, (unsigned)Z);
     conv_wg2_kernel<<<grid, W2_THREADS, sm, st>>>(p, dy, x, dW, dbias);
     count_launch();

@@ -718,16 +718,6 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
     if (tid == 0) atomicAdd(dalpha, dv[0]);
 }
 
-// raise the dynamic shared-memory limit of a kernel only when a larger size than ever before is needed
-// (warm-up calls do it; replays / CUDA-graph captures then issue no attribute call)
-template <typename K>
-static void ensure_smem(K kernel, std::atomic<int>& cur, size_t bytes) {
-    if ((int)bytes > cur.load(std::memory_order_relaxed)) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        cur.store((int)bytes, std::memory_order_relaxed);
-    }
-}
-
 template <typename T>
 static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, const float* x2, const float* W4,
                       const float* b4, const float* PA, const float* alpha, void* y, double* ssum, double* ssq,
@@ -737,15 +727,15 @@ static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, c
         constexpr int VP = VPad<20>::VP, DP = VPad<20>::DP;
         const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 20 * VP + (size_t)g.R * 20 * DP + g.CT * g.R + g.CT * 2 + 2 * g.R * 20);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
-        static std::atomic<int> cur{48 * 1024};
-        ensure_smem(ctrgc_fwd_kernel<T, 20>, cur, sm);
+        static SmemLimit lim;
+        ensure_smem(ctrgc_fwd_kernel<T, 20>, lim, sm);
         ctrgc_fwd_kernel<T, 20><<<grid, 256, sm, st>>>(g, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)y, ssum, ssq);
     } else {
         constexpr int VP = VPad<25>::VP, DP = VPad<25>::DP;
         const size_t sm = sizeof(float) * ((size_t)g.K * g.CT * 25 * VP + (size_t)g.R * 25 * DP + g.CT * g.R + g.CT * 2 + 2 * g.R * 25);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_fwd: shared memory %zu too large (R=%d)", sm, g.R);
-        static std::atomic<int> cur{48 * 1024};
-        ensure_smem(ctrgc_fwd_kernel<T, 25>, cur, sm);
+        static SmemLimit lim;
+        ensure_smem(ctrgc_fwd_kernel<T, 25>, lim, sm);
         ctrgc_fwd_kernel<T, 25><<<grid, 256, sm, st>>>(g, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)y, ssum, ssq);
     }
     count_launch();
@@ -769,13 +759,13 @@ static int launch_bwd_mma(const CtrgcP& g0, int V, const Opnd& go, const void* x
     if (sm > 227 * 1024 || g.R > 128 || (g.R & 1)) return 0;
     dim3 grid(cdiv(g.Cout, g.CT), g.N);
     if (V == 20) {
-        static std::atomic<int> cur{48 * 1024};
-        ensure_smem(ctrgc_bwd_mma_kernel<20>, cur, sm);
+        static SmemLimit lim;
+        ensure_smem(ctrgc_bwd_mma_kernel<20>, lim, sm);
         ctrgc_bwd_mma_kernel<20><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns,
                                                                 dx1, dx2, dW4, db4, dPA, dalpha);
     } else {
-        static std::atomic<int> cur{48 * 1024};
-        ensure_smem(ctrgc_bwd_mma_kernel<25>, cur, sm);
+        static SmemLimit lim;
+        ensure_smem(ctrgc_bwd_mma_kernel<25>, lim, sm);
         ctrgc_bwd_mma_kernel<25><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns,
                                                                 dx1, dx2, dW4, db4, dPA, dalpha);
     }
@@ -795,8 +785,8 @@ static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, co
         const size_t sm = sizeof(float) * ((size_t)g.CT * 20 * VP + 2 * (size_t)g.CT * 20 * DP + (size_t)g.R * 20 * DP +
                                            g.CT * g.R + 64 + 2 * g.R * 20);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
-        static std::atomic<int> cur{48 * 1024};
-        ensure_smem(ctrgc_bwd_kernel<T, 20>, cur, sm);
+        static SmemLimit lim;
+        ensure_smem(ctrgc_bwd_kernel<T, 20>, lim, sm);
         ctrgc_bwd_kernel<T, 20><<<grid, 256, sm, st>>>(g, go, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)dx3, dx3ns,
                                                        dx1, dx2, dW4, db4, dPA, dalpha);
     } else {
@@ -804,8 +794,8 @@ static int launch_bwd(const CtrgcP& g, int V, const Opnd& go, const void* x3, co
         const size_t sm = sizeof(float) * ((size_t)g.CT * 25 * VP + 2 * (size_t)g.CT * 25 * DP + (size_t)g.R * 25 * DP +
                                            g.CT * g.R + 64 + 2 * g.R * 25);
         TG_REQUIRE(sm <= 227 * 1024, "ctrgc_bwd: shared memory %zu too large (R=%d)", sm, g.R);
-        static std::atomic<int> cur{48 * 1024};
-        ensure_smem(ctrgc_bwd_kernel<T, 25>, cur, sm);
+        static SmemLimit lim;
+        ensure_smem(ctrgc_bwd_kernel<T, 25>, lim, sm);
         ctrgc_bwd_kernel<T, 25><<<grid, 256, sm, st>>>(g, go, (const T*)x3, x1, x2, W4, b4, PA, alpha, (T*)dx3, dx3ns,
                                                        dx1, dx2, dW4, db4, dPA, dalpha);
     }

@@ -704,16 +704,7 @@ ctrgc_fwd_tc_kernel(CtcP p, const bf16* __restrict__ x3, const float* __restrict
     if (tid == 0 && hdr->error) printf("tamgcn: ctrgc_fwd(tcgen05) pipeline timeout in block %d\n", blockIdx.x);
 }
 
-static int ctc_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int ctc_num_sms() { return num_sms(); }
 
 static bool ctc_disabled() {
     static int v = -1;
@@ -816,11 +807,8 @@ int ctrgc_fwd_tc(const void* x3, long long x3ns, int N, int Cout, int T, int V, 
     if (grid > p.n_tiles) grid = p.n_tiles;
 #define CTC_LAUNCH(VV, CC)                                                                                              \
     do {                                                                                                                \
-        static int cur = 48 * 1024;                                                                                     \
-        if ((int)sm > cur) {                                                                                            \
-            cudaFuncSetAttribute(ctrgc_fwd_tc_kernel<VV, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);    \
-            cur = (int)sm;                                                                                              \
-        }                                                                                                               \
+        static SmemLimit lim;                                                                                           \
+        ensure_smem(ctrgc_fwd_tc_kernel<VV, CC>, lim, sm);                                                              \
         ctrgc_fwd_tc_kernel<VV, CC><<<grid, CTC_THREADS, sm, st>>>(p, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)y, ssum, ssq); \
     } while (0)
     const int CT = p.P * p.G;

@@ -446,16 +446,7 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
     if (tid == 0 && hdr->error) printf("tamgcn: ctrgc_fwd(tc3) pipeline timeout in block %d\n", blockIdx.x);
 }
 
-static int c3_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int c3_num_sms() { return num_sms(); }
 
 static bool c3_disabled() {
     static int v = -1;
@@ -504,11 +495,8 @@ int ctrgc_fwd_tc3(const void* x3, long long x3ns, int N, int Cout, int T, int V,
     const size_t sm = (size_t)off + 1024;
     int grid = c3_num_sms();
     if (grid > p.n_tiles) grid = p.n_tiles;
-    static int cur = 48 * 1024;
-    if ((int)sm > cur) {
-        cudaFuncSetAttribute(ctrgc_fwd_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        cur = (int)sm;
-    }
+    static SmemLimit lim;
+    ensure_smem(ctrgc_fwd_tc3_kernel, lim, sm);
     ctrgc_fwd_tc3_kernel<<<grid, C3_THREADS, sm, st>>>(p, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)y, ssum, ssq);
     count_launch();
     const int rc = check_launch("ctrgc_fwd(tc3)");

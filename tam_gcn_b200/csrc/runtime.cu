@@ -1,6 +1,7 @@
 // runtime.cu — error reporting, launch accounting, version.  No device memory is ever owned here.
 #include "common.cuh"
 #include <atomic>
+#include <mutex>
 
 namespace tamgcn {
 
@@ -24,6 +25,33 @@ int check_launch(const char* what) {
         return -2;
     }
     return 0;
+}
+
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= TG_MAX_DEVICES) ? 0 : dev;
+}
+
+int num_sms() {
+    static std::atomic<int> n[TG_MAX_DEVICES];
+    const int dev = current_device();
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        n[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+void raise_smem_limit(const void* kernel, SmemLimit& lim, int dev, size_t bytes) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)bytes > lim.cur[dev].load(std::memory_order_relaxed)) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        lim.cur[dev].store((int)bytes, std::memory_order_release);
+    }
 }
 
 }  // namespace tamgcn

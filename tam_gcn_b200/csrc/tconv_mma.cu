@@ -378,16 +378,7 @@ static bool tm_disabled() {
     }
     return v == 1;
 }
-static int tm_num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int tm_num_sms() { return num_sms(); }
 static bool tm_al8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 static int tm_vec(const Opnd& o, int V) {
     bool ok = (V % 4 == 0) && (o.pns % 4 == 0) && tm_al8(o.p);
@@ -464,13 +455,6 @@ static bool tm_setup(TmP& p, const tamgcn_conv_geom* g, int kind, size_t& smem) 
     return true;
 }
 
-template <typename K>
-static void tm_ensure_smem(K kernel, int& cur, size_t bytes) {
-    if ((int)bytes > cur) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        cur = (int)bytes;
-    }
-}
 
 // compile-time (channel count, 8-wide position tiles per row) from the run-time shape
 template <typename F>
@@ -509,8 +493,8 @@ int tconv_mma_fwd_dgrad(const tamgcn_conv_geom* g, int kind, const Opnd& in, con
     Opnd mo = mask ? *mask : plain_opnd(nullptr, 0);
     tm_dispatch(CB, NTW, [&](auto cb, auto ntw) {
         constexpr int CB_ = decltype(cb)::value, NTW_ = decltype(ntw)::value;
-        static int cur = 48 * 1024;
-        tm_ensure_smem(tconv_mma_kernel<CB_, NTW_>, cur, sm);
+        static SmemLimit lim;
+        ensure_smem(tconv_mma_kernel<CB_, NTW_>, lim, sm);
         tconv_mma_kernel<CB_, NTW_><<<(int)grid, TM_THREADS, sm, st>>>(p, in, W, bias, (bf16*)out, mo, mask ? 1 : 0, s1, s2);
     });
     count_launch();
@@ -530,12 +514,12 @@ int tconv_mma_wgrad(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, fl
     tm_dispatch(CB, NTW, [&](auto cb, auto ntw) {
         constexpr int CB_ = decltype(cb)::value, NTW_ = decltype(ntw)::value;
         if (g->k == 5) {
-            static int cur = 48 * 1024;
-            tm_ensure_smem(tconv_wgrad_mma_kernel<CB_, NTW_, 5>, cur, sm);
+            static SmemLimit lim;
+            ensure_smem(tconv_wgrad_mma_kernel<CB_, NTW_, 5>, lim, sm);
             tconv_wgrad_mma_kernel<CB_, NTW_, 5><<<(int)grid, TM_THREADS, sm, st>>>(p, dy, x, dW, db);
         } else {
-            static int cur = 48 * 1024;
-            tm_ensure_smem(tconv_wgrad_mma_kernel<CB_, NTW_, 3>, cur, sm);
+            static SmemLimit lim;
+            ensure_smem(tconv_wgrad_mma_kernel<CB_, NTW_, 3>, lim, sm);
             tconv_wgrad_mma_kernel<CB_, NTW_, 3><<<(int)grid, TM_THREADS, sm, st>>>(p, dy, x, dW, db);
         }
     });

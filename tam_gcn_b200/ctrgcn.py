@@ -270,25 +270,21 @@ class Model(nn.Module):
 
     def _trunk(self, x):
         from . import get_act_dtype
-        if x.dim() == 3:
-            N, T, VC = x.shape
-            x = x.view(N, T, self.num_point, -1).permute(0, 3, 1, 2).contiguous().unsqueeze(-1)
-        N, C, T, V, M = x.size()
-        x = x.permute(0, 4, 3, 1, 2).contiguous().view(N, M * V * C, T)
-        x = self.data_bn(x)
-        x = x.view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)
-        dt = self.act_dtype or get_act_dtype()
-        if x.dtype != dt:
-            x = x.to(dt)
+        # permute + data_bn + permute + cast: one kernel (csrc/head.cu), the input is read in place through its strides
+        M = x.shape[4] if x.dim() == 5 else 1
+        x = Fn.DataBnFn.apply(x, self.data_bn, self.num_point, False, self.act_dtype or get_act_dtype(),
+                              self.data_bn.weight, self.data_bn.bias)
+        N = x.shape[0] // M
         for i in range(1, 11):
             x = getattr(self, 'l%d' % i)(x)
         return x, N, M
 
     def forward(self, x):
         x, N, M = self._trunk(x)
-        x = x.float().view(N, M, x.size(1), -1).mean(3).mean(1)
-        x = self.drop_out(x)
-        return self.fc(x)
+        if isinstance(self.drop_out, nn.Dropout) and self.training and self.drop_out.p > 0:
+            # dropout between pooling and classifier (models/ctrgcn.py:346): pool with the kernel, ATen dropout + linear
+            return self.fc(self.drop_out(Fn.PoolFcFn.apply(x, M, None, None)))
+        return Fn.PoolFcFn.apply(x, M, self.fc.weight, self.fc.bias)
 
     def extract_feature(self, x):
         x, N, M = self._trunk(x)

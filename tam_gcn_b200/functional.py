@@ -16,7 +16,13 @@ produces a tensor, tiny coefficient kernels turn them into per-channel (scale, s
 backward affine (A, B, C), and the consumer kernel applies them while loading (`ops.Opnd`).
 
 No arithmetic on activations happens in Python/ATen here; the only torch ops are allocations, the
-packing (cat/stack) of a few KB of parameters, and O(C) coefficient algebra.
+packing (cat/stack) of a few KB of parameters when no `params.ParamStore` owns them, and O(C) negations of
+BatchNorm coefficients.
+
+Parameter gradients: by default every backward returns them to autograd (fresh zero-initialised accumulators).
+Inside `ParamStore.direct_grads()` (the engine's training step) the kernels accumulate straight into the store's
+flat gradient buffer — the slice that mirrors the parameter (or the whole pack of adjacent parameters) — and
+autograd gets None for them; that buffer is what the optimiser kernel and the NCCL all-reduce consume.
 """
 import torch
 import torch.nn as nn
@@ -25,12 +31,49 @@ from . import arena, ops
 from .ops import Opnd, RES_NONE, RES_IDENTITY, RES_AFFINE
 
 
+_sink = None          # params.ParamStore while its direct_grads() context is active
+
+
 # ------------------------------------------------------------------------------------------------
 # small helpers
 # ------------------------------------------------------------------------------------------------
-def _check_input(x):
+class _GradOut:
+    """Destination of the parameter gradients of one backward call.
+
+    `buf(t)` returns the accumulator for the gradient of `t` (a parameter or a pack of adjacent parameters): the
+    mirroring slice of the active ParamStore's gradient buffer (already cleared for the step) or a fresh zeroed
+    tensor.  `ret(g, t)` is what the autograd Function must return for it: None when the kernels wrote into the
+    store, `g` otherwise."""
+
+    def __init__(self, like):
+        self.like = like
+        self.sink = _sink
+        self.direct = set()
+
+    def buf(self, t, shape=None):
+        if t is None:
+            return None
+        if self.sink is not None:
+            g = self.sink.grad_view(t)
+            if g is not None:
+                self.direct.add(t.data_ptr())
+                return g if shape is None else g.view(shape)
+        return _zeros(tuple(t.shape) if shape is None else shape, self.like, torch.float32)
+
+    def is_direct(self, t):
+        return t is not None and t.data_ptr() in self.direct
+
+    def ret(self, g, t):
+        return None if (t is None or self.is_direct(t)) else g
+
+
+def _require_cuda(x):
     if not x.is_cuda:
         raise RuntimeError('tam_gcn_b200 modules run on CUDA (sm_100a) only; there is no CPU path')
+
+
+def _check_input(x):
+    _require_cuda(x)
     if x.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError('tam_gcn_b200 supports float32 / bfloat16 activations, got %s' % x.dtype)
     if x.dim() != 4:
@@ -73,6 +116,38 @@ def _packed(mod, key, params, shape):
     return flat.view(shape)
 
 
+def _ctrgc_group_lists(convs, extra=None):
+    """Parameter lists of the packs of K CTRGC modules (+ the unit_gcn down conv appended to conv3)."""
+    w3 = [c.conv3.weight for c in convs]
+    b3 = [c.conv3.bias for c in convs]
+    if extra is not None:
+        w3.append(extra.weight)
+        b3.append(extra.bias)
+    return {'W12': [c.conv1.weight for c in convs] + [c.conv2.weight for c in convs],
+            'b12': [c.conv1.bias for c in convs] + [c.conv2.bias for c in convs],
+            'W3': w3, 'b3': b3,
+            'W4': [c.conv4.weight for c in convs], 'b4': [c.conv4.bias for c in convs]}
+
+
+def pack_groups(mod):
+    """[(owner module, key, [parameters])] — the parameter packs `mod` itself asks for (params.ParamStore lays them
+    out adjacently so `_packed` never copies).  Sub-modules are visited separately by the caller."""
+    kind = type(mod).__name__
+    out = []
+    if kind == 'unit_gcn' and hasattr(mod, 'convs'):
+        convs = list(mod.convs)
+        for key, ps in _ctrgc_group_lists(convs, mod.down[0] if getattr(mod, 'has_down', False) else None).items():
+            out.append((convs[0], key, ps))
+    elif kind == 'CTRGC' and hasattr(mod, 'conv4'):
+        for key, ps in _ctrgc_group_lists([mod]).items():
+            out.append((mod, key, ps))
+    elif kind == 'MultiScale_TemporalConv' and hasattr(mod, 'num_dil'):
+        heads = [mod.branches[j][0] for j in range(mod.num_dil + 1)]
+        out.append((mod, 'Wh', [c.weight for c in heads]))
+        out.append((mod, 'bh', [c.bias for c in heads]))
+    return [(o, k, ps) for o, k, ps in out if all(p is not None for p in ps)]
+
+
 def _w2(conv):
     """Conv2d weight (Cout, Cin, k, 1) -> (Cout, Cin*k) fp32 view."""
     w = conv.weight
@@ -95,6 +170,16 @@ def _bias(conv, like):
     return conv.bias
 
 
+def _bn_train(bns):
+    """Common `training` flag of the BatchNorms fused into one kernel (a model in train() with single BatchNorm
+    layers put in eval() — the freeze-BN idiom — is honoured per layer; a mixed group cannot be fused)."""
+    t = bns[0].training
+    for b in bns:
+        if b.training != t:
+            raise NotImplementedError('BatchNorm layers fused in one kernel must share their train/eval mode')
+    return bool(t)
+
+
 def _bn_group(bns):
     m, e = bns[0].momentum, bns[0].eps
     for b in bns:
@@ -113,34 +198,78 @@ class _BnCoef:
         self.scale, self.shift, self.mean, self.invstd = self.t[0], self.t[1], self.t[2], self.t[3]
 
 
-def _bn_forward(bns, slices, coef, stats, count, train):
-    """Finalize BatchNorms `bns` (channel ranges `slices` of the concatenated coefficient rows)."""
+def _bn_forward(bns, slices, coef, stats, count, train, coefs=None):
+    """Finalize BatchNorms `bns` in ONE launch.  Either they are channel ranges `slices` of one concatenated
+    coefficient table `coef` with one (sum, sumsq) pair `stats`, or (coefs=[...]) each has its own table and its own
+    entry of the list `stats`."""
     m, e = _bn_group(bns)
     descs = []
-    for bn, sl in zip(bns, slices):
+    for i, (bn, sl) in enumerate(zip(bns, slices)):
+        cf = coef if coefs is None else coefs[i]
+        st = stats if (coefs is None or stats is None) else stats[i]
         d = dict(gamma=bn.weight, beta=bn.bias, rmean=bn.running_mean, rvar=bn.running_var,
                  nbt=bn.num_batches_tracked if train else None,
-                 scale=coef.scale[sl], shift=coef.shift[sl], mean=coef.mean[sl], invstd=coef.invstd[sl])
+                 scale=cf.scale[sl], shift=cf.shift[sl], mean=cf.mean[sl], invstd=cf.invstd[sl])
         if train:
-            d['sum'], d['sumsq'] = stats[0][sl], stats[1][sl]
+            d['sum'], d['sumsq'] = st[0][sl], st[1][sl]
         descs.append(d)
     ops.bn_finalize(descs, count, m, e, train)
 
 
 class _BnBwd:
-    """Backward affine dY = A*dYhat + B*Y + C of a group of BatchNorms, plus dgamma / dbeta."""
+    """Backward affine dY = A*dYhat + B*Y + C of a group of BatchNorms, plus dgamma / dbeta.
+    `abc`: optional (3, C) storage for the A / B / C rows (a slice of a wider coefficient table)."""
 
-    def __init__(self, C, like):
-        self.t = torch.empty(5, C, device=like.device, dtype=torch.float32)
-        self.A, self.B, self.C, self.dgamma, self.dbeta = self.t[0], self.t[1], self.t[2], self.t[3], self.t[4]
+    def __init__(self, C, like, abc=None):
+        if abc is None:
+            self.t = torch.empty(5, C, device=like.device, dtype=torch.float32)
+            self.A, self.B, self.C, self.dgamma, self.dbeta = self.t[0], self.t[1], self.t[2], self.t[3], self.t[4]
+        else:
+            self.t = torch.empty(2, C, device=like.device, dtype=torch.float32)
+            self.A, self.B, self.C = abc
+            self.dgamma, self.dbeta = self.t[0], self.t[1]
 
 
-def _bn_backward(bns, slices, coef, bw, s1, s2, count, train):
+def _identity_coef_table(mod, Cw, KC, like):
+    """(3, Cw) operand coefficients (a, b, c) whose first KC channels are the identity (1, 0, 0): the cotangent of the
+    concatenated conv3|down output, where only the `down` channels carry a BatchNorm backward.  Cached on the module
+    (per device); the down rows are rewritten by bn_bwd_coef in every backward, the identity rows never change."""
+    cache = mod.__dict__.setdefault('_tamgcn_coef3', {})
+    key = (like.device, Cw, KC)
+    t = cache.get(key)
+    if t is None:
+        t = torch.zeros(3, Cw, device=like.device, dtype=torch.float32)
+        t[0, :KC] = 1.0
+        if not (like.is_cuda and torch.cuda.is_current_stream_capturing()):
+            cache[key] = t
+    return t
+
+
+def _bn_backward(bns, slices, coef, bw, s1, s2, count, train, go=None, per=None):
+    """Backward coefficients of a group of BatchNorms in ONE launch (channel ranges `slices` of shared tables, or
+    per=[(coef, bw, s1, s2), ...] with one entry per BatchNorm); dgamma / dbeta go to the rows of `bw`, or — for
+    parameters owned by the active ParamStore — straight into its gradient buffer (`go`: the call's _GradOut)."""
     descs = []
-    for bn, sl in zip(bns, slices):
-        descs.append(dict(s1=s1[sl], s2=s2[sl], gamma=bn.weight, mean=coef.mean[sl], invstd=coef.invstd[sl],
-                          A=bw.A[sl], B=bw.B[sl], Cc=bw.C[sl], dgamma=bw.dgamma[sl], dbeta=bw.dbeta[sl]))
+    for i, (bn, sl) in enumerate(zip(bns, slices)):
+        cf, b_, a1, a2 = (coef, bw, s1, s2) if per is None else per[i]
+        dg, db = b_.dgamma[sl], b_.dbeta[sl]
+        if go is not None and go.sink is not None:
+            gw, gb = go.sink.grad_view(bn.weight), go.sink.grad_view(bn.bias)
+            if gw is not None and gb is not None:
+                dg, db = gw, gb
+                go.direct.add(bn.weight.data_ptr())
+                go.direct.add(bn.bias.data_ptr())
+        descs.append(dict(s1=a1[sl], s2=a2[sl], gamma=bn.weight, mean=cf.mean[sl], invstd=cf.invstd[sl],
+                          A=b_.A[sl], B=b_.B[sl], Cc=b_.C[sl], dgamma=dg, dbeta=db))
     ops.bn_bwd_coef(descs, count, train)
+
+
+def _bwd_opnd(P, Y, bw, train, sl=None):
+    """dY = A*dYhat + B*Y + C as a lazy operand; in eval mode B = C = 0 and Y is not read at all."""
+    A, B, Cc = (bw.A, bw.B, bw.C) if sl is None else (bw.A[sl], bw.B[sl], bw.C[sl])
+    if train:
+        return Opnd(P, Y, a=A, b=B, c=Cc)
+    return Opnd(P, None, a=A)
 
 
 def _full(sl_c):
@@ -162,33 +291,38 @@ def _ctrgc_pack(convs, like, extra=None):
     for c in convs:
         _w2(c.conv1), _w2(c.conv2), _w2(c.conv3), _w2(c.conv4)                                # dtype checks
     own = convs[0]                                                                            # the packs hang off the first CTRGC
-    W12 = _packed(own, 'W12', [c.conv1.weight for c in convs] + [c.conv2.weight for c in convs], (2 * K * R, Cin))
-    b12 = _packed(own, 'b12', [_bias(c.conv1, like) for c in convs] + [_bias(c.conv2, like) for c in convs], (2 * K * R,))
-    w3 = [c.conv3.weight for c in convs]
-    b3 = [_bias(c.conv3, like) for c in convs]
+    gl = _ctrgc_group_lists(convs, extra)
     Cw = K * Cout
     if extra is not None:
         _w2(extra)
-        w3.append(extra.weight)
-        b3.append(_bias(extra, like))
         Cw += extra.weight.shape[0]
-    W3 = _packed(own, 'W3', w3, (Cw, Cin))                                                    # (K*Cout [+Cd], Cin)
-    b3 = _packed(own, 'b3', b3, (Cw,))
-    W4 = _packed(own, 'W4', [c.conv4.weight for c in convs], (K, Cout, R))
-    b4 = _packed(own, 'b4', [_bias(c.conv4, like) for c in convs], (K, Cout))
+    zb = lambda ps, cs: [p if p is not None else torch.zeros(c.weight.shape[0], device=like.device) for p, c in zip(ps, cs)]
+    c12 = [c.conv1 for c in convs] + [c.conv2 for c in convs]
+    c3 = [c.conv3 for c in convs] + ([extra] if extra is not None else [])
+    W12 = _packed(own, 'W12', gl['W12'], (2 * K * R, Cin))
+    b12 = _packed(own, 'b12', zb(gl['b12'], c12), (2 * K * R,))
+    W3 = _packed(own, 'W3', gl['W3'], (Cw, Cin))                                              # (K*Cout [+Cd], Cin)
+    b3 = _packed(own, 'b3', zb(gl['b3'], c3), (Cw,))
+    W4 = _packed(own, 'W4', gl['W4'], (K, Cout, R))
+    b4 = _packed(own, 'b4', zb(gl['b4'], [c.conv4 for c in convs]), (K, Cout))
     return K, R, Cin, Cout, W12, b12, W3, b3, W4, b4
 
 
-def _ctrgc_unpack_grads(convs, K, R, Cout, dW12, db12, dW3, db3, dW4, db4):
-    """Per-module gradient views, in the order conv1.w, conv1.b, conv2.w, conv2.b, conv3.w, conv3.b, conv4.w, conv4.b."""
+def _ctrgc_unpack_grads(convs, K, R, Cout, go, packs, dW12, db12, dW3, db3, dW4, db4):
+    """Per-module gradient views, in the order conv1.w, conv1.b, conv2.w, conv2.b, conv3.w, conv3.b, conv4.w, conv4.b
+    (None where the kernels accumulated straight into the ParamStore's gradient buffer)."""
+    W12, b12, W3, b3, W4, b4 = packs
     out = []
+    n12, nb12, n3, nb3, n4, nb4 = (go.is_direct(t) for t in (W12, b12, W3, b3, W4, b4))
     for i, c in enumerate(convs):
-        out += [dW12[i * R:(i + 1) * R].view_as(c.conv1.weight), db12[i * R:(i + 1) * R] if c.conv1.bias is not None else None,
-                dW12[(K + i) * R:(K + i + 1) * R].view_as(c.conv2.weight),
-                db12[(K + i) * R:(K + i + 1) * R] if c.conv2.bias is not None else None,
-                dW3[i * Cout:(i + 1) * Cout].view_as(c.conv3.weight),
-                db3[i * Cout:(i + 1) * Cout] if c.conv3.bias is not None else None,
-                dW4[i].view_as(c.conv4.weight), db4[i] if c.conv4.bias is not None else None]
+        out += [None if n12 else dW12[i * R:(i + 1) * R].view_as(c.conv1.weight),
+                None if (nb12 or c.conv1.bias is None) else db12[i * R:(i + 1) * R],
+                None if n12 else dW12[(K + i) * R:(K + i + 1) * R].view_as(c.conv2.weight),
+                None if (nb12 or c.conv2.bias is None) else db12[(K + i) * R:(K + i + 1) * R],
+                None if n3 else dW3[i * Cout:(i + 1) * Cout].view_as(c.conv3.weight),
+                None if (nb3 or c.conv3.bias is None) else db3[i * Cout:(i + 1) * Cout],
+                None if n4 else dW4[i].view_as(c.conv4.weight),
+                None if (nb4 or c.conv4.bias is None) else db4[i]]
     return out
 
 
@@ -219,9 +353,10 @@ class UnitGcnFn(torch.autograd.Function):
     def forward(ctx, x, mod, *params):
         x = _check_input(x)
         N, Cin, T, V = x.shape
-        train = mod.training
         convs = list(mod.convs)
         has_down = mod.has_down
+        tr_g, tr_o = _bn_train([mod.bn]), _bn_train([mod.offset_conv[1]])
+        tr_d = _bn_train([mod.down[1]]) if has_down else False
         K, R, Cin_w, Cout, W12, b12, W3, b3, W4, b4 = _ctrgc_pack(convs, x, mod.down[0] if has_down else None)
         if Cin_w != Cin:
             raise ValueError('unit_gcn: input has %d channels, module expects %d' % (Cin, Cin_w))
@@ -238,25 +373,23 @@ class UnitGcnFn(torch.autograd.Function):
         # conv3 of the K subsets (+ down conv) in one pass over x
         Cw = KC + (Cout if has_down else 0)
         xw = _empty((N, Cw, T, V), x)
-        stats = _zeros((6, Cout), x, torch.float64) if train else None   # rows: down(sum,sq), bn(sum,sq), offset(sum,sq)
+        stats = _zeros((6, Cout), x, torch.float64) if (tr_g or tr_o or tr_d) else None
+        # rows: down(sum,sq), bn(sum,sq), offset(sum,sq)
         pk3 = _pack(W3, 1, x)
-        ops.conv_fwd(x, W3, b3, xw, stats=(stats[0], stats[1]) if (train and has_down) else None, stat_c0=KC,
-                     wpack=pk3[0])
+        ops.conv_fwd(x, W3, b3, xw, stats=(stats[0], stats[1]) if tr_d else None, stat_c0=KC, wpack=pk3[0])
         # fused topology refinement + aggregation (+ BN statistics of y0)
         y0 = _empty((N, Cout, T, V), x)
         ops.ctrgc_fwd(xw[:, :KC], x12[:, :K * R], x12[:, K * R:], W4, b4, PA, alpha, y0,
-                      stats=(stats[2], stats[3]) if train else None)
+                      stats=(stats[2], stats[3]) if tr_g else None)
         cg = _BnCoef(Cout, x)
         cd = _BnCoef(Cout, x) if has_down else None
-        if has_down:
-            if train:
-                _bn_forward([mod.down[1]], [_full(Cout)], cd, (stats[0], stats[1]), count, True)
-                _bn_forward([mod.bn], [_full(Cout)], cg, (stats[2], stats[3]), count, True)
-            else:
-                _bn_forward([mod.down[1]], [_full(Cout)], cd, None, count, False)
-                _bn_forward([mod.bn], [_full(Cout)], cg, None, count, False)
+        if has_down and tr_d == tr_g:
+            _bn_forward([mod.down[1], mod.bn], [slice(0, Cout), slice(0, Cout)], None,
+                        [(stats[0], stats[1]), (stats[2], stats[3])] if tr_g else None, count, tr_g, coefs=[cd, cg])
         else:
-            _bn_forward([mod.bn], [_full(Cout)], cg, (stats[2], stats[3]) if train else None, count, train)
+            if has_down:
+                _bn_forward([mod.down[1]], [_full(Cout)], cd, (stats[0], stats[1]) if tr_d else None, count, tr_d)
+            _bn_forward([mod.bn], [_full(Cout)], cg, (stats[2], stats[3]) if tr_g else None, count, tr_g)
         # offset branch: z = W_o (res - y) + b_o, with res - y formed while loading
         nsg = -cg.scale
         if has_down:
@@ -272,33 +405,35 @@ class UnitGcnFn(torch.autograd.Function):
         Wo, bo = _w2(oc), _bias(oc, x)
         z = _empty((N, Cout, T, V), x)
         pko = _pack(Wo, 1, x)
-        ops.conv_fwd(diff, Wo, bo, z, stats=(stats[4], stats[5]) if train else None, wpack=pko[0])
+        ops.conv_fwd(diff, Wo, bo, z, stats=(stats[4], stats[5]) if tr_o else None, wpack=pko[0])
         co = _BnCoef(Cout, x)
-        _bn_forward([mod.offset_conv[1]], [_full(Cout)], co, (stats[4], stats[5]) if train else None, count, train)
+        _bn_forward([mod.offset_conv[1]], [_full(Cout)], co, (stats[4], stats[5]) if tr_o else None, count, tr_o)
         out = _empty((N, Cout, T, V), x)
         ops.gcn_epilogue_fwd(y0, cg.scale, cg.shift, z, co.scale, co.shift, res_mode, r, sr, hr, out)
 
-        ctx.mod, ctx.train, ctx.dims = mod, train, (N, Cin, Cout, T, V, K, R)
+        ctx.mod, ctx.train, ctx.dims = mod, (tr_g, tr_o, tr_d), (N, Cin, Cout, T, V, K, R)
         ctx.res_mode = res_mode
         ctx.diff = diff
         ctx.coefs = (cg, cd, co)
-        ctx.packed = (W12, W3, W4, b4, PA, Wo, pk3[1], pko[1])
+        ctx.packed = (W12, b12, W3, b3, W4, b4, PA, Wo, pk3[1], pko[1])
         ctx.save_for_backward(x, m, x12, xw, y0, z, out)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        mod, train = ctx.mod, ctx.train
+        mod = ctx.mod
+        tr_g, tr_o, tr_d = ctx.train
         N, Cin, Cout, T, V, K, R = ctx.dims
         x, m, x12, xw, y0, z, out = ctx.saved_tensors
         cg, cd, co = ctx.coefs
-        W12, W3, W4, b4, PA, Wo, pk3d, pkod = ctx.packed
+        W12, b12, W3, b3, W4, b4, PA, Wo, pk3d, pkod = ctx.packed
         has_down = cd is not None
         res_mode = ctx.res_mode
         KC, count = K * Cout, N * T * V
         g = g.contiguous()
         if g.dtype != x.dtype:
             g = g.to(x.dtype)
+        go = _GradOut(x)
         sb = _zeros((6, Cout), x, torch.float64)      # rows: offset(s1,s2), bn(s1,s2), down(s1,s2)
 
         # tail: ReLU mask, tanh', BN_o backward sums
@@ -306,11 +441,13 @@ class UnitGcnFn(torch.autograd.Function):
         DZ = _empty(g.shape, x)
         ops.gcn_epilogue_bwd(g, out, z, co.scale, co.shift, G, DZ, sb[0], sb[1])
         bo_ = _BnBwd(Cout, x)
-        _bn_backward([mod.offset_conv[1]], [_full(Cout)], co, bo_, sb[0], sb[1], count, train)
-        dz = Opnd(DZ, z, a=bo_.A, b=bo_.B, c=bo_.C)
+        obn = mod.offset_conv[1]
+        _bn_backward([obn], [_full(Cout)], co, bo_, sb[0], sb[1], count, tr_o, go)
+        dz = _bwd_opnd(DZ, z, bo_, tr_o)
         # offset conv backward
-        dWo = _zeros(Wo.shape, x, torch.float32)
-        dbo = _zeros((Cout,), x, torch.float32)
+        oc = mod.offset_conv[0]
+        dWo = go.buf(oc.weight, Wo.shape)
+        dbo = go.buf(oc.bias) if oc.bias is not None else _zeros((Cout,), x, torch.float32)
         ops.conv_wgrad(dz, ctx.diff, dWo, dbo)
         DD = _empty(g.shape, x)
         ops.conv_dgrad(dz, Wo, DD, wpack=pkod)
@@ -327,49 +464,53 @@ class UnitGcnFn(torch.autograd.Function):
             dres = None
             ops.gcn_mid_bwd(G, DD, None, y0, None, sb[2], sb[3], None, None)
         bg = _BnBwd(Cout, x)
-        bd = _BnBwd(Cout, x) if has_down else None
-        _bn_backward([mod.bn], [_full(Cout)], cg, bg, sb[2], sb[3], count, train)
+        bd = None
         if has_down:
-            _bn_backward([mod.down[1]], [_full(Cout)], cd, bd, sb[4], sb[5], count, train)
+            tab = _identity_coef_table(mod, Cw, KC, x)
+            bd = _BnBwd(Cout, x, abc=(tab[0, KC:], tab[1, KC:], tab[2, KC:]))
+            if tr_d == tr_g:
+                _bn_backward([mod.bn, mod.down[1]], [_full(Cout), _full(Cout)], None, None, None, None, count, tr_g, go,
+                             per=[(cg, bg, sb[2], sb[3]), (cd, bd, sb[4], sb[5])])
+            else:
+                _bn_backward([mod.bn], [_full(Cout)], cg, bg, sb[2], sb[3], count, tr_g, go)
+                _bn_backward([mod.down[1]], [_full(Cout)], cd, bd, sb[4], sb[5], count, tr_d, go)
+        else:
+            _bn_backward([mod.bn], [_full(Cout)], cg, bg, sb[2], sb[3], count, tr_g, go)
         # fused CTRGC backward
-        dy = Opnd(G, y0, a=bg.A, b=bg.B, c=bg.C)
+        dy = _bwd_opnd(G, y0, bg, tr_g)
         dx12 = _zeros(x12.shape, x, torch.float32)
-        dW4 = _zeros(W4.shape, x, torch.float32)
-        db4 = _zeros(b4.shape, x, torch.float32)
-        dPA = _zeros(PA.shape, x, torch.float32)
-        dalpha = _zeros((1,), x, torch.float32)
+        dW4, db4 = go.buf(W4), go.buf(b4)
+        dPA = go.buf(mod.PA, PA.shape) if mod.adaptive else _zeros(PA.shape, x, torch.float32)
+        dalpha = go.buf(mod.alpha)
         ops.ctrgc_bwd(dy, xw[:, :KC], x12[:, :K * R], x12[:, K * R:], W4, b4, PA, mod.alpha, dxw[:, :KC],
                       dx12[:, :K * R], dx12[:, K * R:], dW4, db4, dPA, dalpha)
         # conv1/conv2 backward on the T-mean
-        dW12 = _zeros(W12.shape, x, torch.float32)
-        db12 = _zeros((W12.shape[0],), x, torch.float32)
+        dW12, db12 = go.buf(W12), go.buf(b12)
         ops.conv_wgrad(dx12, m, dW12, db12)
         dm = _empty(m.shape, x, torch.float32)
         ops.conv_dgrad(dx12, W12, dm)
         # conv3 (+down) backward: one wgrad and one dgrad over the concatenated channels
         if has_down:
-            a = torch.ones(Cw, device=x.device, dtype=torch.float32)
-            b = torch.zeros(Cw, device=x.device, dtype=torch.float32)
-            c = torch.zeros(Cw, device=x.device, dtype=torch.float32)
-            a[KC:], b[KC:], c[KC:] = bd.A, bd.B, bd.C
-            dxw_op = Opnd(dxw, xw, a=a, b=b, c=c)
+            dxw_op = Opnd(dxw, xw, a=tab[0], b=tab[1], c=tab[2])
         else:
             dxw_op = Opnd(dxw)
-        dW3 = _zeros(W3.shape, x, torch.float32)
-        db3 = _zeros((Cw,), x, torch.float32)
+        dW3, db3 = go.buf(W3), go.buf(b3)
         ops.conv_wgrad(dxw_op, x, dW3, db3)
         dx = _empty(x.shape, x)
         ops.conv_dgrad(dxw_op, W3, dx, addend=dres, bcast=dm, bcast_scale=1.0 / T, wpack=pk3d)
 
-        grads = _ctrgc_unpack_grads(list(mod.convs), K, R, Cout, dW12, db12, dW3, db3, dW4, db4)
+        grads = _ctrgc_unpack_grads(list(mod.convs), K, R, Cout, go, (W12, b12, W3, b3, W4, b4), dW12, db12, dW3, db3,
+                                    dW4, db4)
         if has_down:
-            d0 = mod.down[0]
-            grads += [dW3[KC:].view_as(d0.weight), db3[KC:] if d0.bias is not None else None, bd.dgamma, bd.dbeta]
-        oc = mod.offset_conv[0]
-        grads += [dWo.view_as(oc.weight), dbo if oc.bias is not None else None, bo_.dgamma, bo_.dbeta,
-                  bg.dgamma, bg.dbeta, dalpha]
+            d0, d1 = mod.down[0], mod.down[1]
+            n3, nb3 = go.is_direct(W3), go.is_direct(b3)
+            grads += [None if n3 else dW3[KC:].view_as(d0.weight), None if (nb3 or d0.bias is None) else db3[KC:],
+                      go.ret(bd.dgamma, d1.weight), go.ret(bd.dbeta, d1.bias)]
+        grads += [go.ret(dWo.view_as(oc.weight), oc.weight), go.ret(dbo, oc.bias), go.ret(bo_.dgamma, obn.weight),
+                  go.ret(bo_.dbeta, obn.bias), go.ret(bg.dgamma, mod.bn.weight), go.ret(bg.dbeta, mod.bn.bias),
+                  go.ret(dalpha, mod.alpha)]
         if mod.adaptive:
-            grads.append(dPA)
+            grads.append(go.ret(dPA, mod.PA))
         return (dx, None) + tuple(grads)
 
 
@@ -396,7 +537,7 @@ class CtrgcFn(torch.autograd.Function):
         y = _empty((N, Cout, T, V), x)
         ops.ctrgc_fwd(x3, x12[:, :R], x12[:, R:], W4, b4, PA, al, y)
         ctx.mod, ctx.dims = mod, (N, Cin, Cout, T, V, R)
-        ctx.packed = (W12, W3, W4, b4, PA, al, pk3[1])
+        ctx.packed = (W12, b12, W3, b3, W4, b4, PA, al, pk3[1])
         ctx.save_for_backward(x, m, x12, x3)
         ctx.a_shape, ctx.alpha_shape = A.shape, alpha.shape
         return y
@@ -406,27 +547,25 @@ class CtrgcFn(torch.autograd.Function):
         mod = ctx.mod
         N, Cin, Cout, T, V, R = ctx.dims
         x, m, x12, x3 = ctx.saved_tensors
-        W12, W3, W4, b4, PA, al, pk3d = ctx.packed
+        W12, b12, W3, b3, W4, b4, PA, al, pk3d = ctx.packed
         g = g.contiguous().to(x.dtype)
+        go = _GradOut(x)
         dx3 = _empty(x3.shape, x)
         dx12 = _zeros(x12.shape, x, torch.float32)
-        dW4 = _zeros(W4.shape, x, torch.float32)
-        db4 = _zeros(b4.shape, x, torch.float32)
+        dW4, db4 = go.buf(W4), go.buf(b4)
         dPA = _zeros(PA.shape, x, torch.float32)
         dalpha = _zeros((1,), x, torch.float32)
         ops.ctrgc_bwd(Opnd(g), x3, x12[:, :R], x12[:, R:], W4, b4, PA, al, dx3, dx12[:, :R], dx12[:, R:], dW4, db4,
                       dPA, dalpha)
-        dW12 = _zeros(W12.shape, x, torch.float32)
-        db12 = _zeros((2 * R,), x, torch.float32)
+        dW12, db12 = go.buf(W12), go.buf(b12)
         ops.conv_wgrad(dx12, m, dW12, db12)
         dm = _empty(m.shape, x, torch.float32)
         ops.conv_dgrad(dx12, W12, dm)
-        dW3 = _zeros(W3.shape, x, torch.float32)
-        db3 = _zeros((Cout,), x, torch.float32)
+        dW3, db3 = go.buf(W3), go.buf(b3)
         ops.conv_wgrad(dx3, x, dW3, db3)
         dx = _empty(x.shape, x)
         ops.conv_dgrad(dx3, W3, dx, bcast=dm, bcast_scale=1.0 / T, wpack=pk3d)
-        grads = _ctrgc_unpack_grads([mod], 1, R, Cout, dW12, db12, dW3, db3, dW4, db4)
+        grads = _ctrgc_unpack_grads([mod], 1, R, Cout, go, (W12, b12, W3, b3, W4, b4), dW12, db12, dW3, db3, dW4, db4)
         return (dx, dPA.reshape(ctx.a_shape), dalpha.reshape(ctx.alpha_shape), None) + tuple(grads)
 
 
@@ -438,6 +577,15 @@ def _conv_geom(conv):
     if conv.kernel_size[1] != 1 or conv.stride[1] != 1 or conv.padding[1] != 0 or conv.groups != 1:
         raise NotImplementedError('only (k x 1) ungrouped temporal convolutions are supported')
     return k, s, d, p
+
+
+def _conv_wgrad_to(go, conv, dy, xop, like, geom=(1, 1, 1, 0)):
+    """Weight / bias gradient of `conv` into the call's gradient destination; returns (dW, db) as autograd wants them."""
+    W = _w2(conv)
+    dW = go.buf(conv.weight, W.shape)
+    db = go.buf(conv.bias) if conv.bias is not None else _zeros((W.shape[0],), like, torch.float32)
+    ops.conv_wgrad(dy, xop, dW, db, *geom)
+    return go.ret(dW.view_as(conv.weight), conv.weight), go.ret(db, conv.bias)
 
 
 class ConvBnFn(torch.autograd.Function):
@@ -471,18 +619,16 @@ class ConvBnFn(torch.autograd.Function):
         x, raw = ctx.saved_tensors
         N, Cout, To, V = raw.shape
         g = g.contiguous().to(x.dtype)
+        go = _GradOut(x)
         sb = _zeros((2, Cout), x, torch.float64)
         ops.tcn_epilogue_bwd(g, None, False, raw, None, None, sb[0], sb[1], None)
         bw = _BnBwd(Cout, x)
-        _bn_backward([bn], [_full(Cout)], ctx.cf, bw, sb[0], sb[1], N * To * V, train)
-        dy = Opnd(g, raw, a=bw.A, b=bw.B, c=bw.C)
-        W = _w2(conv)
-        dW = _zeros(W.shape, x, torch.float32)
-        db = _zeros((Cout,), x, torch.float32)
-        ops.conv_wgrad(dy, x, dW, db, k, s, d, p)
+        _bn_backward([bn], [_full(Cout)], ctx.cf, bw, sb[0], sb[1], N * To * V, train, go)
+        dy = _bwd_opnd(g, raw, bw, train)
+        gW, gb = _conv_wgrad_to(go, conv, dy, x, x, (k, s, d, p))
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dy, W, dx, k, s, d, p, wpack=ctx.pkd)
-        return dx, None, None, dW.view_as(conv.weight), (db if conv.bias is not None else None), bw.dgamma, bw.dbeta
+        ops.conv_dgrad(dy, _w2(conv), dx, k, s, d, p, wpack=ctx.pkd)
+        return dx, None, None, gW, gb, go.ret(bw.dgamma, bn.weight), go.ret(bw.dbeta, bn.bias)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -517,12 +663,14 @@ class MsTcnFn(torch.autograd.Function):
     def forward(ctx, x, r_in, mod, res_kind, res_mod, relu, *params):
         x = _check_input(x)
         N, Cin, T, V = x.shape
-        train = mod.training
         nd, Cb, s = mod.num_dil, mod.branch_channels, mod.stride
         nb = nd + 2
         Cout, Ch = nb * Cb, (nd + 1) * Cb
         To = _conv_out_len(T, 1, s, 1, 0)
         r_src = x if r_in is None else _check_input(r_in)
+        head_bns = [mod.branches[j][1] for j in range(nd + 1)]
+        final_bns = [mod.branches[j][3].bn for j in range(nd)] + [mod.branches[nd][4], mod.branches[nd + 1][1]]
+        tr_h, tr_u = _bn_train(head_bns), _bn_train(final_bns)
 
         # all 1x1 branch heads that keep T in one pass over x
         heads = [mod.branches[j][0] for j in range(nd + 1)]
@@ -531,20 +679,20 @@ class MsTcnFn(torch.autograd.Function):
         Wh = _packed(mod, 'Wh', [c.weight for c in heads], ((nd + 1) * Cb, Cin))
         bh = _packed(mod, 'bh', [_bias(c, x) for c in heads], ((nd + 1) * Cb,))
         h = _empty((N, Ch, T, V), x)
-        st_h = _zeros((2, Ch), x, torch.float64) if train else None
+        st_h = _zeros((2, Ch), x, torch.float64) if tr_h else None
         pkh = _pack(Wh, 1, x)
         ops.conv_fwd(x, Wh, bh, h, stats=st_h, wpack=pkh[0])
         u = _empty((N, Cout, To, V), x)
-        st_u = _zeros((2, Cout), x, torch.float64) if train else None
+        st_u = _zeros((2, Cout), x, torch.float64) if tr_u else None
         # strided 1x1 branch straight into its slice of u
         c3 = mod.branches[nd + 1][0]
         W3, b3 = _w2(c3), _bias(c3, x)
         pk3 = _pack(W3, 1, x)
-        ops.conv_fwd(x, W3, b3, u[:, Ch:], 1, s, 1, 0, stats=(st_u[0][Ch:], st_u[1][Ch:]) if train else None,
+        ops.conv_fwd(x, W3, b3, u[:, Ch:], 1, s, 1, 0, stats=(st_u[0][Ch:], st_u[1][Ch:]) if tr_u else None,
                      wpack=pk3[0])
         ch = _BnCoef(Ch, x)
         sl = [slice(j * Cb, (j + 1) * Cb) for j in range(nb)]
-        _bn_forward([mod.branches[j][1] for j in range(nd + 1)], sl[:nd + 1], ch, st_h, N * T * V, train)
+        _bn_forward(head_bns, sl[:nd + 1], ch, st_h, N * T * V, tr_h)
         geoms = []
         for j in range(nd):
             tc = mod.branches[j][3].conv
@@ -554,51 +702,59 @@ class MsTcnFn(torch.autograd.Function):
             pkt = _pack(_w2(tc), k, x, cs)
             geoms.append((k, cs, d, p, pkt[1]))
             ops.conv_fwd(Opnd(h[:, sl[j]], a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), _w2(tc), _bias(tc, x),
-                         u[:, sl[j]], k, cs, d, p, stats=(st_u[0][sl[j]], st_u[1][sl[j]]) if train else None,
+                         u[:, sl[j]], k, cs, d, p, stats=(st_u[0][sl[j]], st_u[1][sl[j]]) if tr_u else None,
                          wpack=pkt[0])
         if _conv_out_len(T, 3, s, 1, 1) != To:
             raise ValueError('MultiScale_TemporalConv: max-pool branch output length differs')
         ops.maxpool_fwd(Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), u[:, sl[nd]], s,
-                        stats=(st_u[0][sl[nd]], st_u[1][sl[nd]]) if train else None)
+                        stats=(st_u[0][sl[nd]], st_u[1][sl[nd]]) if tr_u else None)
         cu = _BnCoef(Cout, x)
-        final_bns = [mod.branches[j][3].bn for j in range(nd)] + [mod.branches[nd][4], mod.branches[nd + 1][1]]
-        _bn_forward(final_bns, sl, cu, st_u, N * To * V, train)
-        # residual
+        # residual (its BatchNorm is finalized in the same launch as the branch BatchNorms)
         cr = r_raw = None
+        tr_r = False
         if res_kind == 'conv':
             rk, rs, rd, rp = _conv_geom(res_mod.conv)
             if _conv_out_len(r_src.shape[2], rk, rs, rd, rp) != To or res_mod.conv.weight.shape[0] != Cout:
                 raise ValueError('residual branch shape mismatch')
+            tr_r = res_mod.bn.training
             r_raw = _empty((N, Cout, To, V), x)
-            st_r = _zeros((2, Cout), x, torch.float64) if res_mod.bn.training else None
+            st_r = _zeros((2, Cout), x, torch.float64) if tr_r else None
             pkr = _pack(_w2(res_mod.conv), rk, x, rs)
             ops.conv_fwd(r_src, _w2(res_mod.conv), _bias(res_mod.conv, x), r_raw, rk, rs, rd, rp, stats=st_r,
                          wpack=pkr[0])
             cr = _BnCoef(Cout, x)
-            _bn_forward([res_mod.bn], [_full(Cout)], cr, st_r, N * To * V, res_mod.bn.training)
+            if tr_r == tr_u:
+                _bn_forward(final_bns + [res_mod.bn], sl + [_full(Cout)], None, [st_u] * nb + [st_r], N * To * V, tr_u,
+                            coefs=[cu] * nb + [cr])
+            else:
+                _bn_forward(final_bns, sl, cu, st_u, N * To * V, tr_u)
+                _bn_forward([res_mod.bn], [_full(Cout)], cr, st_r, N * To * V, tr_r)
             res_mode, r, sr, hr = RES_AFFINE, r_raw, cr.scale, cr.shift
-        elif res_kind == 'identity':
-            if r_src.shape != (N, Cout, To, V):
-                raise ValueError('identity residual shape mismatch')
-            res_mode, r, sr, hr = RES_IDENTITY, r_src, None, None
         else:
-            res_mode, r, sr, hr = RES_NONE, None, None, None
+            _bn_forward(final_bns, sl, cu, st_u, N * To * V, tr_u)
+            if res_kind == 'identity':
+                if r_src.shape != (N, Cout, To, V):
+                    raise ValueError('identity residual shape mismatch')
+                res_mode, r, sr, hr = RES_IDENTITY, r_src, None, None
+            else:
+                res_mode, r, sr, hr = RES_NONE, None, None, None
         out = _empty((N, Cout, To, V), x)
         ops.tcn_epilogue_fwd(u, cu.scale, cu.shift, res_mode, r, sr, hr, relu, out)
 
-        ctx.mod, ctx.res_mod, ctx.res_kind, ctx.relu, ctx.train = mod, res_mod, res_kind, relu, train
+        ctx.mod, ctx.res_mod, ctx.res_kind, ctx.relu, ctx.train = mod, res_mod, res_kind, relu, (tr_h, tr_u, tr_r)
         ctx.geoms, ctx.coefs = geoms, (ch, cu, cr)
-        ctx.packed = (Wh, W3, pkh[1], pk3[1], pkr[1] if res_kind == 'conv' else None)
+        ctx.packed = (Wh, bh, W3, pkh[1], pk3[1], pkr[1] if res_kind == 'conv' else None)
         ctx.r_is_x = r_in is None
         ctx.save_for_backward(x, r_src if res_kind == 'conv' else None, h, u, r_raw, out if relu else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        mod, res_mod, res_kind, relu, train = ctx.mod, ctx.res_mod, ctx.res_kind, ctx.relu, ctx.train
+        mod, res_mod, res_kind, relu = ctx.mod, ctx.res_mod, ctx.res_kind, ctx.relu
+        tr_h, tr_u, tr_r = ctx.train
         x, r_src, h, u, r_raw, out = ctx.saved_tensors
         ch, cu, cr = ctx.coefs
-        Wh, W3, pkhd, pk3d, pkrd = ctx.packed
+        Wh, bh, W3, pkhd, pk3d, pkrd = ctx.packed
         N, Cin, T, V = x.shape
         nd, Cb, s = mod.num_dil, mod.branch_channels, mod.stride
         nb = nd + 2
@@ -606,17 +762,28 @@ class MsTcnFn(torch.autograd.Function):
         To = u.shape[2]
         sl = [slice(j * Cb, (j + 1) * Cb) for j in range(nb)]
         g = g.contiguous().to(x.dtype)
+        go = _GradOut(x)
 
         sb = _zeros((3, Cout), x, torch.float64)
         G = _empty(g.shape, x) if relu else None
         ops.tcn_epilogue_bwd(g, out, relu, u, r_raw, G, sb[0], sb[1], sb[2] if r_raw is not None else None)
         Gt = G if relu else g
+        head_bns = [mod.branches[j][1] for j in range(nd + 1)]
         final_bns = [mod.branches[j][3].bn for j in range(nd)] + [mod.branches[nd][4], mod.branches[nd + 1][1]]
         bu = _BnBwd(Cout, x)
-        _bn_backward(final_bns, sl, cu, bu, sb[0], sb[1], N * To * V, train)
+        br = None
+        if res_kind == 'conv' and tr_r == tr_u:
+            br = _BnBwd(Cout, x)
+            _bn_backward(final_bns + [res_mod.bn], sl + [_full(Cout)], None, None, None, None, N * To * V, tr_u, go,
+                         per=[(cu, bu, sb[0], sb[1])] * nb + [(cr, br, sb[0], sb[2])])
+        else:
+            _bn_backward(final_bns, sl, cu, bu, sb[0], sb[1], N * To * V, tr_u, go)
+            if res_kind == 'conv':
+                br = _BnBwd(Cout, x)
+                _bn_backward([res_mod.bn], [_full(Cout)], cr, br, sb[0], sb[2], N * To * V, tr_r, go)
 
         def dy_op(c0, c1):
-            return Opnd(Gt[:, c0:c1], u[:, c0:c1], a=bu.A[c0:c1], b=bu.B[c0:c1], c=bu.C[c0:c1])
+            return _bwd_opnd(Gt[:, c0:c1], u[:, c0:c1], bu, tr_u, slice(c0, c1))
 
         DH = _empty(h.shape, x)
         sh = _zeros((2, Ch), x, torch.float64)
@@ -626,65 +793,58 @@ class MsTcnFn(torch.autograd.Function):
             k, cs, d, p, pktd = ctx.geoms[j]
             dyj = dy_op(sl[j].start, sl[j].stop)
             hj = h[:, sl[j]]
-            W = _w2(tc)
-            dW = _zeros(W.shape, x, torch.float32)
-            db = _zeros((Cb,), x, torch.float32)
-            ops.conv_wgrad(dyj, Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), dW, db, k, cs, d, p)
-            ops.conv_dgrad(dyj, W, DH[:, sl[j]], k, cs, d, p, mask=Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]]),
+            tgrads.append(_conv_wgrad_to(go, tc, dyj, Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), x,
+                                         (k, cs, d, p)))
+            ops.conv_dgrad(dyj, _w2(tc), DH[:, sl[j]], k, cs, d, p, mask=Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]]),
                            stats=(sh[0][sl[j]], sh[1][sl[j]]), wpack=pktd)
-            tgrads.append((dW.view_as(tc.weight), db if tc.bias is not None else None))
         ops.maxpool_bwd(dy_op(sl[nd].start, sl[nd].stop),
                         Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), DH[:, sl[nd]], s,
                         stats=(sh[0][sl[nd]], sh[1][sl[nd]]))
         bh_ = _BnBwd(Ch, x)
-        _bn_backward([mod.branches[j][1] for j in range(nd + 1)], sl[:nd + 1], ch, bh_, sh[0], sh[1], N * T * V, train)
-        dh = Opnd(DH, h, a=bh_.A, b=bh_.B, c=bh_.C)
-        dWh = _zeros(Wh.shape, x, torch.float32)
-        dbh = _zeros((Ch,), x, torch.float32)
+        _bn_backward(head_bns, sl[:nd + 1], ch, bh_, sh[0], sh[1], N * T * V, tr_h, go)
+        dh = _bwd_opnd(DH, h, bh_, tr_h)
+        dWh, dbh = go.buf(Wh), go.buf(bh)
         ops.conv_wgrad(dh, x, dWh, dbh)
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dh, Wh, dx, wpack=pkhd)
+        # identity residual of a stand-alone module: its cotangent is added by the first data-gradient kernel
+        ops.conv_dgrad(dh, Wh, dx, addend=Gt if (res_kind == 'identity' and ctx.r_is_x) else None, wpack=pkhd)
         dy3 = dy_op(Ch, Cout)
-        dW3 = _zeros(W3.shape, x, torch.float32)
-        db3 = _zeros((Cb,), x, torch.float32)
-        ops.conv_wgrad(dy3, x, dW3, db3, 1, s, 1, 0)
+        c3 = mod.branches[nd + 1][0]
+        g3 = _conv_wgrad_to(go, c3, dy3, x, x, (1, s, 1, 0))
         ops.conv_dgrad(dy3, W3, dx, 1, s, 1, 0, addend=dx, wpack=pk3d)
 
         dr = None
         rgrads = []
         if res_kind == 'conv':
-            br = _BnBwd(Cout, x)
-            _bn_backward([res_mod.bn], [_full(Cout)], cr, br, sb[0], sb[2], N * To * V, res_mod.bn.training)
             rk, rs, rd, rp = _conv_geom(res_mod.conv)
-            dyr = Opnd(Gt, r_raw, a=br.A, b=br.B, c=br.C)
+            dyr = _bwd_opnd(Gt, r_raw, br, tr_r)
+            gr = _conv_wgrad_to(go, res_mod.conv, dyr, r_src, x, (rk, rs, rd, rp))
             Wr = _w2(res_mod.conv)
-            dWr = _zeros(Wr.shape, x, torch.float32)
-            dbr = _zeros((Cout,), x, torch.float32)
-            ops.conv_wgrad(dyr, r_src, dWr, dbr, rk, rs, rd, rp)
             if ctx.r_is_x:
                 ops.conv_dgrad(dyr, Wr, dx, rk, rs, rd, rp, addend=dx, wpack=pkrd)
             else:
                 dr = _empty(r_src.shape, x)
                 ops.conv_dgrad(dyr, Wr, dr, rk, rs, rd, rp, wpack=pkrd)
-            rgrads = [dWr.view_as(res_mod.conv.weight), dbr if res_mod.conv.bias is not None else None, br.dgamma,
-                      br.dbeta]
-        elif res_kind == 'identity':
-            if ctx.r_is_x:
-                dx = dx + Gt
-            else:
-                dr = Gt
+            rgrads = [gr[0], gr[1], go.ret(br.dgamma, res_mod.bn.weight), go.ret(br.dbeta, res_mod.bn.bias)]
+        elif res_kind == 'identity' and not ctx.r_is_x:
+            dr = Gt
 
+        nh, nbh = go.is_direct(Wh), go.is_direct(bh)
         grads = []
         for j in range(nd):
             br_ = mod.branches[j]
-            grads += [dWh[sl[j]].view_as(br_[0].weight), dbh[sl[j]] if br_[0].bias is not None else None,
-                      bh_.dgamma[sl[j]], bh_.dbeta[sl[j]], tgrads[j][0], tgrads[j][1], bu.dgamma[sl[j]], bu.dbeta[sl[j]]]
+            grads += [None if nh else dWh[sl[j]].view_as(br_[0].weight),
+                      None if (nbh or br_[0].bias is None) else dbh[sl[j]],
+                      go.ret(bh_.dgamma[sl[j]], br_[1].weight), go.ret(bh_.dbeta[sl[j]], br_[1].bias),
+                      tgrads[j][0], tgrads[j][1],
+                      go.ret(bu.dgamma[sl[j]], br_[3].bn.weight), go.ret(bu.dbeta[sl[j]], br_[3].bn.bias)]
         br_ = mod.branches[nd]
-        grads += [dWh[sl[nd]].view_as(br_[0].weight), dbh[sl[nd]] if br_[0].bias is not None else None,
-                  bh_.dgamma[sl[nd]], bh_.dbeta[sl[nd]], bu.dgamma[sl[nd]], bu.dbeta[sl[nd]]]
+        grads += [None if nh else dWh[sl[nd]].view_as(br_[0].weight),
+                  None if (nbh or br_[0].bias is None) else dbh[sl[nd]],
+                  go.ret(bh_.dgamma[sl[nd]], br_[1].weight), go.ret(bh_.dbeta[sl[nd]], br_[1].bias),
+                  go.ret(bu.dgamma[sl[nd]], br_[4].weight), go.ret(bu.dbeta[sl[nd]], br_[4].bias)]
         br_ = mod.branches[nd + 1]
-        grads += [dW3.view_as(br_[0].weight), db3 if br_[0].bias is not None else None, bu.dgamma[sl[nd + 1]],
-                  bu.dbeta[sl[nd + 1]]]
+        grads += [g3[0], g3[1], go.ret(bu.dgamma[sl[nd + 1]], br_[1].weight), go.ret(bu.dbeta[sl[nd + 1]], br_[1].bias)]
         grads += rgrads
         return (dx, dr, None, None, None, None) + tuple(grads)
 
@@ -721,16 +881,14 @@ class CtgFn(torch.autograd.Function):
         k, s, d, p = ctx.geom
         x, y, Af = ctx.saved_tensors
         g = g.contiguous().to(x.dtype)
+        go = _GradOut(x)
         dy = _empty(y.shape, x)
         dA = _zeros(Af.shape, x, torch.float32)
         ops.graph_agg_bwd(Opnd(g), y, Af, dy, dA)
-        W = _w2(mod.conv)
-        dW = _zeros(W.shape, x, torch.float32)
-        db = _zeros((W.shape[0],), x, torch.float32)
-        ops.conv_wgrad(dy, x, dW, db, k, s, d, p)
+        gW, gb = _conv_wgrad_to(go, mod.conv, dy, x, x, (k, s, d, p))
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dy, W, dx, k, s, d, p, wpack=ctx.pkd)
-        return dx, dA.to(ctx.a_dtype), None, dW.view_as(mod.conv.weight), (db if mod.conv.bias is not None else None)
+        ops.conv_dgrad(dy, _w2(mod.conv), dx, k, s, d, p, wpack=ctx.pkd)
+        return dx, dA.to(ctx.a_dtype), None, gW, gb
 
 
 def st_gcn_params(mod):
@@ -748,7 +906,7 @@ class StGcnFn(torch.autograd.Function):
     def forward(ctx, x, A, mod, *params):
         x = _check_input(x)
         N, Cin, T, V = x.shape
-        train = mod.training
+        tr_a, tr_u = mod.tcn[0].training, mod.tcn[3].training
         K = mod.gcn.kernel_size
         gk, gs, gd, gp = _conv_geom(mod.gcn.conv)
         KC = mod.gcn.conv.weight.shape[0]
@@ -760,31 +918,33 @@ class StGcnFn(torch.autograd.Function):
         pkg = _pack(Wg, gk, x, gs)
         ops.conv_fwd(x, Wg, bg, y, gk, gs, gd, gp, wpack=pkg[0])
         agg = _empty((N, Cout, Tg, V), x)
-        st_a = _zeros((2, Cout), x, torch.float64) if train else None
+        st_a = _zeros((2, Cout), x, torch.float64) if tr_a else None
         ops.graph_agg_fwd(y, Af, agg, stats=st_a)
         ca = _BnCoef(Cout, x)
-        _bn_forward([mod.tcn[0]], [_full(Cout)], ca, st_a, N * Tg * V, train)
+        _bn_forward([mod.tcn[0]], [_full(Cout)], ca, st_a, N * Tg * V, tr_a)
         tc = mod.tcn[2]
         k, s, d, p = _conv_geom(tc)
         To = _conv_out_len(Tg, k, s, d, p)
         u = _empty((N, Cout, To, V), x)
-        st_u = _zeros((2, Cout), x, torch.float64) if train else None
+        st_u = _zeros((2, Cout), x, torch.float64) if tr_u else None
         pkt = _pack(_w2(tc), k, x, s)
         ops.conv_fwd(Opnd(agg, a=ca.scale, c=ca.shift, relu=True), _w2(tc), _bias(tc, x), u, k, s, d, p, stats=st_u,
                      wpack=pkt[0])
         cu = _BnCoef(Cout, x)
-        _bn_forward([mod.tcn[3]], [_full(Cout)], cu, st_u, N * To * V, train)
+        _bn_forward([mod.tcn[3]], [_full(Cout)], cu, st_u, N * To * V, tr_u)
         cr = r_raw = None
+        tr_r = False
         pkr = (None, None)
         if mod.res_kind == 'conv':
             rc = mod.residual[0]
+            tr_r = mod.residual[1].training
             rk, rs, rd, rp = _conv_geom(rc)
             r_raw = _empty((N, Cout, To, V), x)
-            st_r = _zeros((2, Cout), x, torch.float64) if train else None
+            st_r = _zeros((2, Cout), x, torch.float64) if tr_r else None
             pkr = _pack(_w2(rc), rk, x, rs)
             ops.conv_fwd(x, _w2(rc), _bias(rc, x), r_raw, rk, rs, rd, rp, stats=st_r, wpack=pkr[0])
             cr = _BnCoef(Cout, x)
-            _bn_forward([mod.residual[1]], [_full(Cout)], cr, st_r, N * To * V, train)
+            _bn_forward([mod.residual[1]], [_full(Cout)], cr, st_r, N * To * V, tr_r)
             res_mode, r, sr, hr = RES_AFFINE, r_raw, cr.scale, cr.shift
         elif mod.res_kind == 'identity':
             res_mode, r, sr, hr = RES_IDENTITY, x, None, None
@@ -792,65 +952,175 @@ class StGcnFn(torch.autograd.Function):
             res_mode, r, sr, hr = RES_NONE, None, None, None
         out = _empty((N, Cout, To, V), x)
         ops.tcn_epilogue_fwd(u, cu.scale, cu.shift, res_mode, r, sr, hr, True, out)
-        ctx.mod, ctx.train, ctx.coefs, ctx.pkd = mod, train, (ca, cu, cr), (pkg[1], pkt[1], pkr[1])
+        ctx.mod, ctx.train, ctx.coefs, ctx.pkd = mod, (tr_a, tr_u, tr_r), (ca, cu, cr), (pkg[1], pkt[1], pkr[1])
         ctx.save_for_backward(x, y, Af, agg, u, r_raw, out)
         ctx.a_dtype = A.dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
-        mod, train = ctx.mod, ctx.train
+        mod = ctx.mod
+        tr_a, tr_u, tr_r = ctx.train
         ca, cu, cr = ctx.coefs
         x, y, Af, agg, u, r_raw, out = ctx.saved_tensors
         N, Cout, To, V = u.shape
         Tg = agg.shape[2]
         g = g.contiguous().to(x.dtype)
+        go = _GradOut(x)
         sb = _zeros((3, Cout), x, torch.float64)
         G = _empty(g.shape, x)
         ops.tcn_epilogue_bwd(g, out, True, u, r_raw, G, sb[0], sb[1], sb[2] if r_raw is not None else None)
         bu = _BnBwd(Cout, x)
-        _bn_backward([mod.tcn[3]], [_full(Cout)], cu, bu, sb[0], sb[1], N * To * V, train)
+        _bn_backward([mod.tcn[3]], [_full(Cout)], cu, bu, sb[0], sb[1], N * To * V, tr_u, go)
         tc = mod.tcn[2]
         k, s, d, p = _conv_geom(tc)
-        dyu = Opnd(G, u, a=bu.A, b=bu.B, c=bu.C)
-        Wt = _w2(tc)
-        dWt = _zeros(Wt.shape, x, torch.float32)
-        dbt = _zeros((Cout,), x, torch.float32)
-        ops.conv_wgrad(dyu, Opnd(agg, a=ca.scale, c=ca.shift, relu=True), dWt, dbt, k, s, d, p)
+        dyu = _bwd_opnd(G, u, bu, tr_u)
+        gWt, gbt = _conv_wgrad_to(go, tc, dyu, Opnd(agg, a=ca.scale, c=ca.shift, relu=True), x, (k, s, d, p))
         DA = _empty(agg.shape, x)
         sa = _zeros((2, Cout), x, torch.float64)
         pkgd, pktd, pkrd = ctx.pkd
-        ops.conv_dgrad(dyu, Wt, DA, k, s, d, p, mask=Opnd(agg, a=ca.scale, c=ca.shift), stats=(sa[0], sa[1]),
+        ops.conv_dgrad(dyu, _w2(tc), DA, k, s, d, p, mask=Opnd(agg, a=ca.scale, c=ca.shift), stats=(sa[0], sa[1]),
                        wpack=pktd)
         ba = _BnBwd(Cout, x)
-        _bn_backward([mod.tcn[0]], [_full(Cout)], ca, ba, sa[0], sa[1], N * Tg * V, train)
+        _bn_backward([mod.tcn[0]], [_full(Cout)], ca, ba, sa[0], sa[1], N * Tg * V, tr_a, go)
         dy = _empty(y.shape, x)
         dA = _zeros(Af.shape, x, torch.float32)
-        ops.graph_agg_bwd(Opnd(DA, agg, a=ba.A, b=ba.B, c=ba.C), y, Af, dy, dA)
+        ops.graph_agg_bwd(_bwd_opnd(DA, agg, ba, tr_a), y, Af, dy, dA)
         gk, gs, gd, gp = _conv_geom(mod.gcn.conv)
         Wg = _w2(mod.gcn.conv)
-        dWg = _zeros(Wg.shape, x, torch.float32)
-        dbg = _zeros((Wg.shape[0],), x, torch.float32)
-        ops.conv_wgrad(dy, x, dWg, dbg, gk, gs, gd, gp)
+        gWg, gbg = _conv_wgrad_to(go, mod.gcn.conv, dy, x, x, (gk, gs, gd, gp))
         dx = _empty(x.shape, x)
         rgrads = []
         if mod.res_kind == 'conv':
             ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp, wpack=pkgd)
-            rc = mod.residual[0]
+            rc, rb = mod.residual[0], mod.residual[1]
             rk, rs, rd, rp = _conv_geom(rc)
             br = _BnBwd(Cout, x)
-            _bn_backward([mod.residual[1]], [_full(Cout)], cr, br, sb[0], sb[2], N * To * V, train)
-            dyr = Opnd(G, r_raw, a=br.A, b=br.B, c=br.C)
-            Wr = _w2(rc)
-            dWr = _zeros(Wr.shape, x, torch.float32)
-            dbr = _zeros((Cout,), x, torch.float32)
-            ops.conv_wgrad(dyr, x, dWr, dbr, rk, rs, rd, rp)
-            ops.conv_dgrad(dyr, Wr, dx, rk, rs, rd, rp, addend=dx, wpack=pkrd)
-            rgrads = [dWr.view_as(rc.weight), dbr if rc.bias is not None else None, br.dgamma, br.dbeta]
+            _bn_backward([rb], [_full(Cout)], cr, br, sb[0], sb[2], N * To * V, tr_r, go)
+            dyr = _bwd_opnd(G, r_raw, br, tr_r)
+            gWr, gbr = _conv_wgrad_to(go, rc, dyr, x, x, (rk, rs, rd, rp))
+            ops.conv_dgrad(dyr, _w2(rc), dx, rk, rs, rd, rp, addend=dx, wpack=pkrd)
+            rgrads = [gWr, gbr, go.ret(br.dgamma, rb.weight), go.ret(br.dbeta, rb.bias)]
         elif mod.res_kind == 'identity':
             ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp, addend=G, wpack=pkgd)
         else:
             ops.conv_dgrad(dy, Wg, dx, gk, gs, gd, gp, wpack=pkgd)
-        grads = [dWg.view_as(mod.gcn.conv.weight), dbg if mod.gcn.conv.bias is not None else None, ba.dgamma, ba.dbeta,
-                 dWt.view_as(tc.weight), dbt if tc.bias is not None else None, bu.dgamma, bu.dbeta] + rgrads
+        grads = [gWg, gbg, go.ret(ba.dgamma, mod.tcn[0].weight), go.ret(ba.dbeta, mod.tcn[0].bias), gWt, gbt,
+                 go.ret(bu.dgamma, mod.tcn[3].weight), go.ret(bu.dbeta, mod.tcn[3].bias)] + rgrads
         return (dx, dA.to(ctx.a_dtype), None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# network ends: data_bn prologue, pooled classifier head, cross-entropy   (csrc/head.cu)
+# ------------------------------------------------------------------------------------------------
+class DataBnFn(torch.autograd.Function):
+    """Model.forward prologue (models/ctrgcn.py:324-332, models/stgcn.py:168-181): (N,C,T,V,M) or (N,T,V*C) fp32 input
+    -> BatchNorm1d over the (m, v, c) channels (fold_m: over (v, c) with the persons in the batch, ST-GCN) ->
+    (N*M, C, T, V) in the activation dtype.  One kernel each way; the input is read in place through its strides."""
+
+    @staticmethod
+    def forward(ctx, x, bn, num_point, fold_m, act_dtype, *params):
+        _require_cuda(x)
+        if x.dtype != torch.float32:
+            x = x.float()
+        if x.dim() not in (3, 5):
+            raise ValueError('expected (N, C, T, V, M) or (N, T, V*C) input, got shape %s' % (tuple(x.shape),))
+        if not bn.affine or not bn.track_running_stats or bn.momentum is None:
+            raise NotImplementedError('data_bn without affine / running statistics / float momentum is not supported')
+        if x.dim() == 5:
+            N, C, T, V, M = x.shape
+        else:
+            N, T, VC = x.shape
+            V, M = num_point, 1
+            C = VC // V
+        nch = (1 if fold_m else M) * V * C
+        if bn.weight.numel() != nch:
+            raise ValueError('data_bn has %d channels, input needs %d' % (bn.weight.numel(), nch))
+        train = bn.training
+        out = torch.empty((N * M, C, T, V), device=x.device, dtype=act_dtype)
+        save = torch.empty((2, nch), device=x.device, dtype=torch.float32)
+        ops.data_bn_fwd(x, num_point, fold_m, bn, train, out, save[0], save[1])
+        ctx.bn, ctx.num_point, ctx.fold_m, ctx.train = bn, num_point, fold_m, train
+        ctx.save_for_backward(x, save)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, save = ctx.saved_tensors
+        bn = ctx.bn
+        go = _GradOut(x)
+        g = g.contiguous()
+        dgamma, dbeta = go.buf(bn.weight), go.buf(bn.bias)
+        dx = torch.empty(x.shape if x.dim() == 5 else (x.shape[0], x.shape[2] // ctx.num_point, x.shape[1], ctx.num_point, 1),
+                         device=x.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        ops.data_bn_bwd(g, x, ctx.num_point, ctx.fold_m, bn.weight, save[0], save[1], ctx.train, dgamma, dbeta, dx)
+        if dx is not None and x.dim() == 3:                 # (N,C,T,V,1) -> (N,T,V*C)
+            dx = dx[..., 0].permute(0, 2, 3, 1).reshape(x.shape)
+        return dx, None, None, None, None, go.ret(dgamma, bn.weight), go.ret(dbeta, bn.bias)
+
+
+class PoolFcFn(torch.autograd.Function):
+    """logits = Linear(mean over persons and (T, V) of x)  (models/ctrgcn.py:343-348; models/stgcn.py:187-195 with
+    the 1x1 `fcn` conv on the pooled feature being the same linear map).  x: (N*M, C, T, V).
+    weight None: pooling only (returns the (N, C) pooled feature)."""
+
+    @staticmethod
+    def forward(ctx, x, M, weight, bias):
+        x = _check_input(x)
+        NM, C, T, V = x.shape
+        N = NM // M
+        W = None
+        if weight is not None:
+            W = weight.reshape(weight.shape[0], -1)
+            if W.shape[1] != C or W.dtype != torch.float32:
+                raise ValueError('classifier expects %d fp32 input features, got %d' % (W.shape[1], C))
+        pooled = torch.empty((N, C), device=x.device, dtype=torch.float32)
+        logits = torch.empty((N, W.shape[0]), device=x.device, dtype=torch.float32) if W is not None else None
+        ops.pool_fc_fwd(x, M, W, bias, pooled, logits)
+        ctx.M, ctx.xmeta = M, (x.shape, x.dtype)
+        ctx.save_for_backward(pooled, weight, bias)
+        return logits if W is not None else pooled
+
+    @staticmethod
+    def backward(ctx, dl):
+        pooled, weight, bias = ctx.saved_tensors
+        shape, dtype = ctx.xmeta
+        go = _GradOut(pooled)
+        dl = dl.contiguous().float()
+        g = torch.empty(shape, device=pooled.device, dtype=dtype) if ctx.needs_input_grad[0] else None
+        if weight is None:
+            if g is not None:
+                ops.pool_fc_bwd(dl, pooled, None, ctx.M, g, None, None)
+            return g, None, None, None
+        W = weight.reshape(weight.shape[0], -1)
+        dW = go.buf(weight, W.shape)
+        db = go.buf(bias) if bias is not None else None
+        ops.pool_fc_bwd(dl, pooled, W, ctx.M, g, dW, db)
+        return g, None, go.ret(dW.view_as(weight), weight), go.ret(db, bias)
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """nn.CrossEntropyLoss() of the reference's processors (processor/recognition_rgb.py:19,61): mean over the batch of
+    -log softmax(logits)[label]; labels outside [0, K) (e.g. -100) are ignored."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        _require_cuda(logits)
+        logits = logits.contiguous().float()
+        labels = labels.contiguous().long()
+        loss = torch.empty((1,), device=logits.device, dtype=torch.float32)
+        dl = torch.empty_like(logits)
+        ops.softmax_ce_fwd(logits, labels, loss, dl)
+        ctx.save_for_backward(dl)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gl):
+        dl, = ctx.saved_tensors
+        out = torch.empty_like(dl)
+        ops.softmax_ce_bwd(dl, gl.reshape(1).contiguous().float(), out)
+        return out, None
+
+
+def cross_entropy(logits, labels):
+    return CrossEntropyFn.apply(logits, labels)

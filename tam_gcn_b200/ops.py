@@ -7,6 +7,7 @@ is no fallback path — a missing library or a CPU tensor raises.
 Activation arguments may be channel-slice VIEWS of wider contiguous (N, C, T, V) tensors; the sample
 stride is taken from `stride(0)`.
 """
+import contextlib
 import ctypes as C
 
 import torch
@@ -26,6 +27,49 @@ class Opnd:
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- side stream for work that is off the critical path of backward -------------------------------------------------
+# Weight-gradient kernels feed nothing but the optimiser, so inside `side_stream(s)` they are enqueued on `s` (ordered
+# after everything already on the current stream) and the current stream moves on to the next data-gradient kernel.
+# Every tensor such a launch touches is kept referenced until `join_side_stream`, so the caching allocator cannot hand
+# its memory to a later kernel of the main stream while the side stream still reads it.
+class _Side:
+    __slots__ = ('stream', 'keep')
+
+    def __init__(self, stream):
+        self.stream, self.keep = stream, []
+
+
+_side = None
+
+
+@contextlib.contextmanager
+def side_stream(stream):
+    global _side
+    old = _side
+    _side = _Side(stream) if stream is not None else None
+    try:
+        yield
+    finally:
+        if _side is not None and _side.keep:
+            join_side_stream(stream)
+        _side = old
+
+
+def join_side_stream(stream):
+    """Make the current stream wait for the side stream and release the tensors held for it."""
+    if stream is None:
+        return
+    torch.cuda.current_stream().wait_stream(stream)
+    if _side is not None and _side.stream is stream:
+        _side.keep.clear()
+
+
+def _opnd_tensors(o):
+    if torch.is_tensor(o):
+        return (o,)
+    return tuple(t for t in (o.p, o.q, o.a, o.b, o.c) if t is not None)
 
 
 def _dt(t):
@@ -155,7 +199,8 @@ def conv_pack_weights(W, Cout, Cin, k, stride=1, V=0):
 
 
 def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
-    """dW += dY (*) X, dbias += sum dY  (fp32 accumulators, zeroed by the caller)."""
+    """dW += dY (*) X, dbias += sum dY  (fp32 accumulators, zeroed by the caller).  Runs on the side stream when one
+    is active (see `side_stream`)."""
     dyp = dy.p if isinstance(dy, Opnd) else dy
     xp = x.p if isinstance(x, Opnd) else x
     N, Cout, To, V = dyp.shape
@@ -164,9 +209,15 @@ def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
     dyo, xo = _operand(dy, Cout), _operand(x, Cin)
     if xp.dtype != dyp.dtype:
         raise TypeError('conv_wgrad: mixed activation dtypes')
-    _C.check(_C.lib().tamgcn_conv_wgrad(C.byref(g), _dt(dyp), C.byref(dyo), C.byref(xo), _f32(dW, Cout * Cin * k),
-                                        _f32(dbias, Cout if dbias is not None else None), _stream()),
-             'tamgcn_conv_wgrad')
+    args = (C.byref(g), _dt(dyp), C.byref(dyo), C.byref(xo), _f32(dW, Cout * Cin * k),
+            _f32(dbias, Cout if dbias is not None else None))
+    sd = _side
+    if sd is None:
+        _C.check(_C.lib().tamgcn_conv_wgrad(*args, _stream()), 'tamgcn_conv_wgrad')
+        return
+    sd.stream.wait_stream(torch.cuda.current_stream())
+    sd.keep.append(_opnd_tensors(dy) + _opnd_tensors(x) + (dW, dbias))
+    _C.check(_C.lib().tamgcn_conv_wgrad(*args, sd.stream.cuda_stream), 'tamgcn_conv_wgrad')
 
 
 def mean_t(x, m):
@@ -360,3 +411,80 @@ def graph_agg_bwd(dout, y, A, dy, dA):
     _C.check(_C.lib().tamgcn_graph_agg_bwd(_dt(dp), N, K, Cc, T, V, C.byref(do), yp, yns, _f32(A, K * V * V), dyp,
                                            dyns, _f32(dA, K * V * V if dA is not None else None), _stream()),
              'tamgcn_graph_agg_bwd')
+
+
+# ---- network ends and optimiser (csrc/head.cu) ---------------------------------------------------------------------
+def _strides5(x, fold_3d_num_point=None):
+    """Element strides of the (n, c, t, v, m) axes of a 5-D (N,C,T,V,M) or 3-D (N,T,V*C) fp32 input."""
+    if x.dim() == 5:
+        return tuple(x.shape), tuple(x.stride())
+    N, T, VC = x.shape
+    V = fold_3d_num_point
+    Cc = VC // V
+    sn, st, s2 = x.stride()
+    return (N, Cc, T, V, 1), (sn, s2, st, Cc * s2, 0)          # x.view(N,T,V,C).permute(0,3,1,2).unsqueeze(-1)
+
+
+def data_bn_fwd(x, num_point, fold_m, bn, train, out, save_mean, save_invstd):
+    """BatchNorm1d prologue of Model.forward; x: fp32 (N,C,T,V,M) or (N,T,V*C); out: (N*M, C, T, V)."""
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise TypeError('data_bn: expected a CUDA float32 input')
+    (N, Cc, T, V, M), st = _strides5(x, num_point)
+    arr = (_C.i64 * 5)(*st)
+    _C.check(_C.lib().tamgcn_data_bn_fwd(_dt(out), x.data_ptr(), arr, N, Cc, T, V, M, 1 if fold_m else 0, _p(bn.weight),
+                                         _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
+                                         _p(bn.num_batches_tracked) if train else None, float(bn.momentum), float(bn.eps),
+                                         1 if train else 0, _full(out, out.dtype), _f32(save_mean), _f32(save_invstd),
+                                         _stream()), 'tamgcn_data_bn_fwd')
+
+
+def data_bn_bwd(g, x, num_point, fold_m, gamma, mean, invstd, train, dgamma, dbeta, dx):
+    (N, Cc, T, V, M), st = _strides5(x, num_point)
+    arr = (_C.i64 * 5)(*st)
+    _C.check(_C.lib().tamgcn_data_bn_bwd(_dt(g), _full(g, g.dtype), x.data_ptr(), arr, N, Cc, T, V, M, 1 if fold_m else 0,
+                                         _p(gamma), _f32(mean), _f32(invstd), 1 if train else 0, _f32(dgamma), _f32(dbeta),
+                                         _f32(dx), _stream()), 'tamgcn_data_bn_bwd')
+
+
+def pool_fc_fwd(x, M, W, b, pooled, logits):
+    """x: (N*M, C, T, V); pooled (N, C) fp32; logits (N, K) fp32 (W None: pooling only)."""
+    NM, Cc, T, V = x.shape
+    N = NM // M
+    K = W.shape[0] if W is not None else 0
+    _C.check(_C.lib().tamgcn_pool_fc_fwd(_dt(x), _full(x, x.dtype), N, M, Cc, T * V, K, _f32(W, K * Cc if W is not None else None),
+                                         _f32(b), _f32(pooled, N * Cc), _f32(logits), _stream()), 'tamgcn_pool_fc_fwd')
+
+
+def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db):
+    """W None: pooling only (dlogits is the cotangent of pooled, K == C)."""
+    N, K = dlogits.shape
+    Cc = pooled.shape[1]
+    if g is not None:
+        TV = g.shape[2] * g.shape[3]
+        dt = _dt(g)
+    else:
+        TV, dt = 1, _C.F32
+    _C.check(_C.lib().tamgcn_pool_fc_bwd(dt, _f32(dlogits), _f32(pooled), _f32(W, K * Cc if W is not None else None), N, M, Cc, TV, K,
+                                         None if g is None else _full(g, g.dtype), _f32(dW), _f32(db), _stream()),
+             'tamgcn_pool_fc_bwd')
+
+
+def softmax_ce_fwd(logits, labels, loss, dl):
+    N, K = logits.shape
+    if labels.dtype != torch.int64 or not labels.is_contiguous():
+        raise TypeError('softmax_ce: labels must be contiguous int64')
+    _C.check(_C.lib().tamgcn_softmax_ce_fwd(_f32(logits), labels.data_ptr(), N, K, _f32(loss, 1), _f32(dl), _stream()),
+             'tamgcn_softmax_ce_fwd')
+
+
+def softmax_ce_bwd(dl, gloss, out):
+    N, K = dl.shape
+    _C.check(_C.lib().tamgcn_softmax_ce_bwd(_f32(dl), _f32(gloss, 1), N, K, _f32(out), _stream()), 'tamgcn_softmax_ce_bwd')
+
+
+def sgd_step(P, G, Mo, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
+    """In-place SGD over flat fp32 buffers; lr is a 1-element CUDA tensor."""
+    n = P.numel()
+    _C.check(_C.lib().tamgcn_sgd_step(_f32(P), _f32(G, n), _f32(Mo, n), n, _f32(lr, 1), float(momentum),
+                                      float(weight_decay), 1 if nesterov else 0, float(grad_scale), _stream()),
+             'tamgcn_sgd_step')

@@ -92,29 +92,26 @@ class Model(nn.Module):
 
     def _trunk(self, x):
         from . import get_act_dtype
-        if x.dim() == 3:
-            N, T, VC = x.shape
-            x = x.view(N, T, self.num_point, -1).permute(0, 3, 1, 2).contiguous().unsqueeze(-1)
-        N, C, T, V, M = x.size()
-        x = x.permute(0, 4, 3, 1, 2).contiguous().view(N * M, V * C, T)
-        x = self.data_bn(x)
-        x = x.view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)
-        dt = self.act_dtype or get_act_dtype()
-        if x.dtype != dt:
-            x = x.to(dt)
+        # data_bn over (v, c) channels with the persons folded into the batch (models/stgcn.py:174-181): one kernel
+        M = x.shape[4] if x.dim() == 5 else 1
+        x = Fn.DataBnFn.apply(x, self.data_bn, self.num_point, True, self.act_dtype or get_act_dtype(),
+                              self.data_bn.weight, self.data_bn.bias)
+        N = x.shape[0] // M
         for gcn, importance in zip(self.st_gcn_networks, self.edge_importance):
             x, _ = gcn(x, self.A * importance)
-        return x.float(), N, M
+        return x, N, M
 
     def forward(self, x):
         x, N, M = self._trunk(x)
-        x = x.mean(dim=(2, 3), keepdim=True).view(N, M, -1, 1, 1).mean(dim=1)
-        x = self.drop_out(x)
-        # 1x1 classifier on the pooled (N,256,1,1) feature == a linear layer (kept off cuDNN's TF32 default)
-        return F.linear(x.view(N, -1), self.fcn.weight.view(self.fcn.out_channels, -1), self.fcn.bias)
+        if isinstance(self.drop_out, nn.Dropout) and self.training and self.drop_out.p > 0:
+            x = self.drop_out(Fn.PoolFcFn.apply(x, M, None, None))
+            return F.linear(x, self.fcn.weight.view(self.fcn.out_channels, -1), self.fcn.bias)
+        # global pooling + the 1x1 classifier on the pooled (N,256,1,1) feature == pooled linear layer: one kernel
+        return Fn.PoolFcFn.apply(x, M, self.fcn.weight, self.fcn.bias)
 
     def extract_feature(self, x):
         x, N, M = self._trunk(x)
+        x = x.float()
         _, c, t, v = x.size()
         feature = x.view(N, M, c, t, v).permute(0, 2, 3, 4, 1)
         out = torch.einsum('oc,nctv->notv', self.fcn.weight.view(self.fcn.out_channels, -1), x)

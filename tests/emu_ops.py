@@ -272,16 +272,122 @@ def graph_agg_bwd(dout, y, A, dy, dA):
         dA += torch.einsum('nkctv,nctw->kvw', y.float().reshape(N, K, KC // K, T, V), gv)
 
 
+def _x5(x, num_point):
+    """(N, C, T, V, M) fp32 view of the model input (5-D as is, 3-D (N, T, V*C) as models/ctrgcn.py:325-327)."""
+    if x.dim() == 5:
+        return x
+    N, T, VC = x.shape
+    return x.view(N, T, num_point, -1).permute(0, 3, 1, 2).unsqueeze(-1)
+
+
+def _data_bn_rows(x5, fold_m):
+    N, C, T, V, M = x5.shape
+    if fold_m:
+        return x5.permute(0, 4, 3, 1, 2).reshape(N * M, V * C, T)       # models/stgcn.py:175-176
+    return x5.permute(0, 4, 3, 1, 2).reshape(N, M * V * C, T)           # models/ctrgcn.py:329
+
+
+def _rows_to_nchw(y, N, C, T, V, M):
+    return y.reshape(N, M, V, C, T).permute(0, 1, 3, 4, 2).reshape(N * M, C, T, V)
+
+
+def data_bn_fwd(x, num_point, fold_m, bn, train, out, save_mean, save_invstd):
+    x5 = _x5(x, num_point)
+    N, C, T, V, M = x5.shape
+    rows = _data_bn_rows(x5, fold_m).double()
+    if train:
+        mean = rows.mean((0, 2))
+        var = rows.var((0, 2), unbiased=False)
+        cnt = rows.shape[0] * rows.shape[2]
+        m = bn.momentum
+        bn.running_mean.copy_(((1 - m) * bn.running_mean.double() + m * mean).float())
+        bn.running_var.copy_(((1 - m) * bn.running_var.double() + m * var * cnt / max(cnt - 1, 1)).float())
+        bn.num_batches_tracked += 1
+    else:
+        mean, var = bn.running_mean.double(), bn.running_var.double()
+    invstd = 1.0 / torch.sqrt(var + bn.eps)
+    y = (rows - mean.view(1, -1, 1)) * (invstd * bn.weight.double()).view(1, -1, 1) + bn.bias.double().view(1, -1, 1)
+    out.copy_(_rows_to_nchw(y, N, C, T, V, M).to(out.dtype))
+    save_mean.copy_(mean.float())
+    save_invstd.copy_(invstd.float())
+
+
+def data_bn_bwd(g, x, num_point, fold_m, gamma, mean, invstd, train, dgamma, dbeta, dx):
+    x5 = _x5(x, num_point)
+    N, C, T, V, M = x5.shape
+    rows = _data_bn_rows(x5, fold_m).double()
+    grow = g.double().reshape(N, M, C, T, V).permute(0, 1, 4, 2, 3)                    # (N, M, V, C, T)
+    grow = grow.reshape(N * M, V * C, T) if fold_m else grow.reshape(N, M * V * C, T)
+    xh = (rows - mean.double().view(1, -1, 1)) * invstd.double().view(1, -1, 1)
+    s1, s2 = grow.sum((0, 2)), (grow * xh).sum((0, 2))
+    if dgamma is not None:
+        dgamma += s2.float()
+    if dbeta is not None:
+        dbeta += s1.float()
+    if dx is not None:
+        cnt = rows.shape[0] * rows.shape[2]
+        a = (gamma.double() * invstd.double()).view(1, -1, 1)
+        d = a * (grow - (s1 / cnt).view(1, -1, 1) - xh * (s2 / cnt).view(1, -1, 1)) if train else a * grow
+        d = d.reshape(N, M, V, C, T).permute(0, 3, 4, 2, 1)                            # (N, C, T, V, M)
+        dx.copy_(d.float())
+
+
+def pool_fc_fwd(x, M, W, b, pooled, logits):
+    NM, C, T, V = x.shape
+    p = x.float().reshape(NM // M, M, C, T * V).mean(3).mean(1)
+    pooled.copy_(p)
+    if W is not None:
+        logits.copy_(F.linear(p, W, b))
+
+
+def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db):
+    dp = dlogits if W is None else dlogits @ W
+    if dW is not None:
+        dW += dlogits.t() @ pooled
+    if db is not None:
+        db += dlogits.sum(0)
+    if g is not None:
+        NM, C, T, V = g.shape
+        g.copy_((dp / (M * T * V)).view(NM // M, 1, C, 1, 1).expand(NM // M, M, C, T, V).reshape(g.shape).to(g.dtype))
+
+
+def softmax_ce_fwd(logits, labels, loss, dl):
+    valid = (labels >= 0) & (labels < logits.shape[1])
+    cnt = int(valid.sum())
+    lsm = torch.log_softmax(logits.double(), 1)
+    safe = labels.clamp(0, logits.shape[1] - 1)
+    nll = -lsm.gather(1, safe.view(-1, 1)).view(-1) * valid
+    loss.copy_((nll.sum() / cnt).float().reshape(1))
+    if dl is not None:
+        d = lsm.exp()
+        d[torch.arange(len(labels)), safe] -= 1.0
+        dl.copy_((d * valid.view(-1, 1) / cnt).float())
+
+
+def softmax_ce_bwd(dl, gloss, out):
+    out.copy_(dl * gloss.reshape(()))
+
+
+def sgd_step(P, G, Mo, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
+    with torch.no_grad():
+        g = G * grad_scale + weight_decay * P
+        Mo.mul_(momentum).add_(g)
+        P.sub_(float(lr) * (g + momentum * Mo if nesterov else Mo))
+
+
 ALL = ['conv_pack_weights', 'conv_fwd', 'conv_dgrad', 'conv_wgrad', 'mean_t', 'ctrgc_fwd', 'ctrgc_bwd', 'bn_finalize', 'bn_bwd_coef',
        'gcn_epilogue_fwd', 'gcn_epilogue_bwd', 'gcn_mid_bwd', 'tcn_epilogue_fwd', 'tcn_epilogue_bwd', 'maxpool_fwd',
-       'maxpool_bwd', 'graph_agg_fwd', 'graph_agg_bwd']
+       'maxpool_bwd', 'graph_agg_fwd', 'graph_agg_bwd', 'data_bn_fwd', 'data_bn_bwd', 'pool_fc_fwd', 'pool_fc_bwd',
+       'softmax_ce_fwd', 'softmax_ce_bwd', 'sgd_step']
 
 
-def install(monkeypatch):
-    """Route tam_gcn_b200.functional through the emulation (CPU orchestration tests)."""
+def install(monkeypatch=None):
+    """Route tam_gcn_b200.functional through the emulation (CPU orchestration tests).  Without a monkeypatch fixture
+    (spawned worker processes) the attributes are simply overwritten."""
     import tam_gcn_b200.ops as real
     import tam_gcn_b200.functional as Fn
     g = globals()
+    put = monkeypatch.setattr if monkeypatch is not None else setattr
     for name in ALL:
-        monkeypatch.setattr(real, name, g[name])
-    monkeypatch.setattr(Fn, '_check_input', lambda x: x.contiguous())
+        put(real, name, g[name])
+    put(Fn, '_require_cuda', lambda x: None)

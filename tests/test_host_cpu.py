@@ -35,6 +35,17 @@ def test_zero_arena_serves_slices_after_sizing_step():
     assert x2.eq(0).all() and y2.eq(0).all() and z2.eq(0).all() and lo <= z2.data_ptr() < hi
     a.end_step()
     assert not (lo <= a.zeros((2,), torch.float32).data_ptr() < hi)
+    # module-level zeros() serves from the arena made current by use(); a frozen arena never re-allocates
+    assert arena.zeros((3,), torch.float32, 'cpu').eq(0).all()
+    a.freeze()
+    with arena.use(a):
+        a.begin_step()
+        big = arena.zeros((1 << 16,), torch.float32, 'cpu')
+        small = arena.zeros((5,), torch.float32, 'cpu')
+        a.end_step()
+        a.begin_step()
+        assert a.buf.data_ptr() == lo and lo <= small.data_ptr() < hi and not (lo <= big.data_ptr() < hi)
+        a.end_step()
 
 
 def test_packed_parameters_are_views_of_one_buffer():
