@@ -66,6 +66,36 @@ def join_side_stream(stream):
         _side.keep.clear()
 
 
+# ---- algorithmic bytes / FLOPs accounting (bench.py's step-level roofline) -----------------------------------------
+_acct = None
+
+
+@contextlib.contextmanager
+def account(table):
+    """Inside the context every wrapper adds [algorithmic bytes, FLOPs] of its call to table[family]."""
+    global _acct
+    old = _acct
+    _acct = table
+    try:
+        yield table
+    finally:
+        _acct = old
+
+
+def _count(family, nbytes, flops=0):
+    if _acct is not None:
+        e = _acct.setdefault(family, [0, 0])
+        e[0] += int(nbytes)
+        e[1] += int(flops)
+
+
+def _opnd_elems(o):
+    """elements read for a lazy operand (P, plus Q when it has a second term)"""
+    if torch.is_tensor(o):
+        return o.numel()
+    return o.p.numel() * (2 if (o.q is not None and o.b is not None) else 1)
+
+
 def _opnd_tensors(o):
     if torch.is_tensor(o):
         return (o,)
@@ -155,6 +185,10 @@ def conv_fwd(x, W, bias, y, k=1, stride=1, dil=1, pad=0, stats=None, stat_c0=0, 
         ssum, ssq = _f64(stats[0], Cout - stat_c0), _f64(stats[1], Cout - stat_c0)
     _C.check(_C.lib().tamgcn_conv_fwd(C.byref(g), _dt(xp), C.byref(xo), _f32(W, Cout * Cin * k), _p(wpack), _f32(bias), yp, yns,
                                       ssum, ssq, stat_c0, _stream()), 'tamgcn_conv_fwd')
+    if _acct is not None:
+        rows = min(T, To * k)
+        _count('conv_fwd', xp.element_size() * (_opnd_elems(x) * rows // T + y.numel()) + 4 * Cout * Cin * k,
+               2 * N * To * V * Cout * Cin * k)
 
 
 def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, bcast_scale=0.0, mask=None,
@@ -182,6 +216,10 @@ def conv_dgrad(dy, W, dx, k=1, stride=1, dil=1, pad=0, addend=None, bcast=None, 
     _C.check(_C.lib().tamgcn_conv_dgrad(C.byref(g), _dt(dyp), C.byref(dyo), _f32(W, Cout * Cin * k), _p(wpack), dxp, dxns, ap,
                                         ans or 0, _f32(bcast, N * Cin * V if bcast is not None else None),
                                         float(bcast_scale), mo, s1, s2, _stream()), 'tamgcn_conv_dgrad')
+    if _acct is not None:
+        extra = (addend.numel() if addend is not None else 0) + (mask.p.numel() if mask is not None else 0)
+        _count('conv_dgrad', dyp.element_size() * (_opnd_elems(dy) + dx.numel() * min(T, To * k) // T + extra) + 4 * Cout * Cin * k,
+               2 * N * To * V * Cout * Cin * k)
 
 
 def conv_pack_weights(W, Cout, Cin, k, stride=1, V=0):
@@ -211,6 +249,9 @@ def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
         raise TypeError('conv_wgrad: mixed activation dtypes')
     args = (C.byref(g), _dt(dyp), C.byref(dyo), C.byref(xo), _f32(dW, Cout * Cin * k),
             _f32(dbias, Cout if dbias is not None else None))
+    if _acct is not None:
+        _count('conv_wgrad', dyp.element_size() * (_opnd_elems(dy) + _opnd_elems(x) * min(T, To * k) // T) + 4 * Cout * Cin * k,
+               2 * N * To * V * Cout * Cin * k)
     sd = _side
     if sd is None:
         _C.check(_C.lib().tamgcn_conv_wgrad(*args, _stream()), 'tamgcn_conv_wgrad')
@@ -225,6 +266,7 @@ def mean_t(x, m):
     N, Cc, T, V = x.shape
     xp, xns = _act(x)
     _C.check(_C.lib().tamgcn_mean_t(_dt(x), xp, xns, N, Cc, T, V, _f32(m, N * Cc * V), _stream()), 'tamgcn_mean_t')
+    _count('epilogues+maxpool', x.element_size() * x.numel() + 4 * m.numel())
 
 
 def ctrgc_fwd(x3, x1, x2, W4, b4, PA, alpha, y, stats=None):
@@ -244,6 +286,8 @@ def ctrgc_fwd(x3, x1, x2, W4, b4, PA, alpha, y, stats=None):
     _C.check(_C.lib().tamgcn_ctrgc_fwd(_dt(x3), x3p, x3ns, N, Cout, T, V, K, R, x1p, x2p, x12ns,
                                        _f32(W4, K * Cout * R), _f32(b4, K * Cout), _f32(PA, K * V * V),
                                        _f32(alpha, 1), yp, yns, ssum, ssq, _stream()), 'tamgcn_ctrgc_fwd')
+    _count('ctrgc_fwd', x3.element_size() * N * T * V * Cout * (K + 1) + K * 8 * N * R * V + K * 4 * (Cout * R + Cout + V * V),
+           2 * K * N * Cout * T * V * V)
 
 
 def ctrgc_bwd(g, x3, x1, x2, W4, b4, PA, alpha, dx3, dx1, dx2, dW4, db4, dPA, dalpha):
@@ -265,6 +309,8 @@ def ctrgc_bwd(g, x3, x1, x2, W4, b4, PA, alpha, dx3, dx1, dx2, dW4, db4, dPA, da
                                        _f32(alpha, 1), dx3p, dx3ns, d1p, d2p, _f32(dW4, K * Cout * R),
                                        _f32(db4, K * Cout), _f32(dPA, K * V * V), _f32(dalpha, 1), _stream()),
              'tamgcn_ctrgc_bwd')
+    _count('ctrgc_bwd', x3.element_size() * N * T * V * Cout * (1 + 2 * K) + 2 * K * 8 * N * R * V + K * 4 * (Cout * R + Cout + V * V),
+           4 * K * N * Cout * T * V * V)
 
 
 def bn_finalize(descs, count, momentum, eps, train):
@@ -321,6 +367,7 @@ def gcn_epilogue_fwd(y0, sg, hg, z, so, ho, res_mode, r, sr, hr, out):
     _C.check(_C.lib().tamgcn_gcn_epilogue_fwd(_dt(y0), N, Cc, T * V, _full(y0, dt), _f32(sg, Cc), _f32(hg, Cc),
                                               _full(z, dt), _f32(so, Cc), _f32(ho, Cc), res_mode, rp, rns, _f32(sr),
                                               _f32(hr), _full(out, dt), _stream()), 'tamgcn_gcn_epilogue_fwd')
+    _count('epilogues+maxpool', y0.element_size() * y0.numel() * (3 + (1 if r is not None else 0)))
 
 
 def gcn_epilogue_bwd(g, out, z, so, ho, G, DZ, s1o, s2o):
@@ -329,6 +376,7 @@ def gcn_epilogue_bwd(g, out, z, so, ho, G, DZ, s1o, s2o):
     _C.check(_C.lib().tamgcn_gcn_epilogue_bwd(_dt(g), N, Cc, T * V, _full(g, dt), _full(out, dt), _full(z, dt),
                                               _f32(so, Cc), _f32(ho, Cc), _full(G, dt), _full(DZ, dt), _f64(s1o, Cc),
                                               _f64(s2o, Cc), _stream()), 'tamgcn_gcn_epilogue_bwd')
+    _count('epilogues+maxpool', g.element_size() * g.numel() * 5)
 
 
 def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d):
@@ -339,6 +387,7 @@ def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d):
     _C.check(_C.lib().tamgcn_gcn_mid_bwd(_dt(G), N, Cc, T * V, _full(G, dt), _full(DD, dt), drp, drns, _full(y0, dt),
                                          rp, rns, _f64(s1g, Cc), _f64(s2g, Cc), _f64(s1d), _f64(s2d), _stream()),
              'tamgcn_gcn_mid_bwd')
+    _count('epilogues+maxpool', G.element_size() * G.numel() * (4 + (1 if dr is not None else 0) + (1 if r is not None else 0)))
 
 
 def tcn_epilogue_fwd(u, su, hu, res_mode, r, sr, hr, relu, out):
@@ -349,6 +398,7 @@ def tcn_epilogue_fwd(u, su, hu, res_mode, r, sr, hr, relu, out):
     _C.check(_C.lib().tamgcn_tcn_epilogue_fwd(_dt(u), N, Cc, T * V, up, uns, _f32(su, Cc), _f32(hu, Cc), res_mode, rp,
                                               rns, _f32(sr), _f32(hr), 1 if relu else 0, _full(out, dt), _stream()),
              'tamgcn_tcn_epilogue_fwd')
+    _count('epilogues+maxpool', u.element_size() * u.numel() * (2 + (1 if r is not None else 0)))
 
 
 def tcn_epilogue_bwd(g, out, relu, u, r, G, s1, s2u, s2r):
@@ -359,6 +409,8 @@ def tcn_epilogue_bwd(g, out, relu, u, r, G, s1, s2u, s2r):
     _C.check(_C.lib().tamgcn_tcn_epilogue_bwd(_dt(g), N, Cc, T * V, _full(g, dt), _p(out), 1 if relu else 0, up, uns,
                                               rp, rns, _p(G), _f64(s1, Cc), _f64(s2u, Cc), _f64(s2r), _stream()),
              'tamgcn_tcn_epilogue_bwd')
+    _count('epilogues+maxpool', g.element_size() * g.numel() * (2 + (1 if out is not None else 0) + (1 if G is not None else 0) +
+                                                               (1 if r is not None else 0)))
 
 
 def maxpool_fwd(x, y, stride, stats=None):
@@ -372,6 +424,7 @@ def maxpool_fwd(x, y, stride, stats=None):
         ssum, ssq = _f64(stats[0], Cc), _f64(stats[1], Cc)
     _C.check(_C.lib().tamgcn_maxpool_fwd(_dt(xp), N, Cc, T, To, V, stride, C.byref(xo), yp, yns, ssum, ssq,
                                          _stream()), 'tamgcn_maxpool_fwd')
+    _count('epilogues+maxpool', xp.element_size() * (xp.numel() + y.numel()))
 
 
 def maxpool_bwd(dy, x, dh, stride, stats=None):
@@ -385,6 +438,7 @@ def maxpool_bwd(dy, x, dh, stride, stats=None):
         s1, s2 = _f64(stats[0], Cc), _f64(stats[1], Cc)
     _C.check(_C.lib().tamgcn_maxpool_bwd(_dt(dyp), N, Cc, T, To, V, stride, C.byref(dyo), C.byref(xo), dhp, dhns, s1,
                                          s2, _stream()), 'tamgcn_maxpool_bwd')
+    _count('epilogues+maxpool', dyp.element_size() * (_opnd_elems(dy) + x.p.numel() + dh.numel()))
 
 
 def graph_agg_fwd(y, A, out, stats=None):
@@ -399,6 +453,7 @@ def graph_agg_fwd(y, A, out, stats=None):
         ssum, ssq = _f64(stats[0], Cc), _f64(stats[1], Cc)
     _C.check(_C.lib().tamgcn_graph_agg_fwd(_dt(y), N, K, Cc, T, V, yp, yns, _f32(A, K * V * V), op, ons, ssum, ssq,
                                            _stream()), 'tamgcn_graph_agg_fwd')
+    _count('graph_agg', y.element_size() * (y.numel() + out.numel()), 2 * N * KC * T * V * V)
 
 
 def graph_agg_bwd(dout, y, A, dy, dA):
@@ -411,6 +466,7 @@ def graph_agg_bwd(dout, y, A, dy, dA):
     _C.check(_C.lib().tamgcn_graph_agg_bwd(_dt(dp), N, K, Cc, T, V, C.byref(do), yp, yns, _f32(A, K * V * V), dyp,
                                            dyns, _f32(dA, K * V * V if dA is not None else None), _stream()),
              'tamgcn_graph_agg_bwd')
+    _count('graph_agg', dp.element_size() * (_opnd_elems(dout) + y.numel() + dy.numel()), 4 * N * K * Cc * T * V * V)
 
 
 # ---- network ends and optimiser (csrc/head.cu) ---------------------------------------------------------------------
@@ -436,6 +492,7 @@ def data_bn_fwd(x, num_point, fold_m, bn, train, out, save_mean, save_invstd):
                                          _p(bn.num_batches_tracked) if train else None, float(bn.momentum), float(bn.eps),
                                          1 if train else 0, _full(out, out.dtype), _f32(save_mean), _f32(save_invstd),
                                          _stream()), 'tamgcn_data_bn_fwd')
+    _count('head+sgd', 4 * x.numel() + out.element_size() * out.numel())
 
 
 def data_bn_bwd(g, x, num_point, fold_m, gamma, mean, invstd, train, dgamma, dbeta, dx):
@@ -444,6 +501,7 @@ def data_bn_bwd(g, x, num_point, fold_m, gamma, mean, invstd, train, dgamma, dbe
     _C.check(_C.lib().tamgcn_data_bn_bwd(_dt(g), _full(g, g.dtype), x.data_ptr(), arr, N, Cc, T, V, M, 1 if fold_m else 0,
                                          _p(gamma), _f32(mean), _f32(invstd), 1 if train else 0, _f32(dgamma), _f32(dbeta),
                                          _f32(dx), _stream()), 'tamgcn_data_bn_bwd')
+    _count('head+sgd', 4 * x.numel() + g.element_size() * g.numel() + (4 * x.numel() if dx is not None else 0))
 
 
 def pool_fc_fwd(x, M, W, b, pooled, logits):
@@ -453,6 +511,7 @@ def pool_fc_fwd(x, M, W, b, pooled, logits):
     K = W.shape[0] if W is not None else 0
     _C.check(_C.lib().tamgcn_pool_fc_fwd(_dt(x), _full(x, x.dtype), N, M, Cc, T * V, K, _f32(W, K * Cc if W is not None else None),
                                          _f32(b), _f32(pooled, N * Cc), _f32(logits), _stream()), 'tamgcn_pool_fc_fwd')
+    _count('head+sgd', x.element_size() * x.numel())
 
 
 def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db):
@@ -467,6 +526,7 @@ def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db):
     _C.check(_C.lib().tamgcn_pool_fc_bwd(dt, _f32(dlogits), _f32(pooled), _f32(W, K * Cc if W is not None else None), N, M, Cc, TV, K,
                                          None if g is None else _full(g, g.dtype), _f32(dW), _f32(db), _stream()),
              'tamgcn_pool_fc_bwd')
+    _count('head+sgd', g.element_size() * g.numel() if g is not None else 0)
 
 
 def softmax_ce_fwd(logits, labels, loss, dl):
@@ -488,3 +548,4 @@ def sgd_step(P, G, Mo, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
     _C.check(_C.lib().tamgcn_sgd_step(_f32(P), _f32(G, n), _f32(Mo, n), n, _f32(lr, 1), float(momentum),
                                       float(weight_decay), 1 if nesterov else 0, float(grad_scale), _stream()),
              'tamgcn_sgd_step')
+    _count('head+sgd', 20 * n)

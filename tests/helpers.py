@@ -136,3 +136,53 @@ def compare(name, res, fx, tol_y, tol_dx, tol_g, tol_buf=None, report=None, tol_
     if report is not None:
         report.append('%-28s y %.2e dx %.2e dW %.2e (%s) buf %.2e' % (name, e_y, e_dx, worst_g, worst_k, worst_b))
     return fails
+
+
+# ---- reference-initialised whole models (fresh init is the regime the benchmark runs in) ---------------------------
+UCLA = dict(num_class=10, num_point=20, num_person=1, graph='graph.ucla.Graph', graph_args=dict(labeling_mode='spatial'))
+NTU = dict(num_class=60, num_point=25, num_person=2, graph='graph.ntu_rgb_d.Graph', graph_args=dict(labeling_mode='spatial'))
+
+
+def wake_dead_paths(model, seed=0):
+    """The reference init leaves alpha = 0, the offset conv = 0 and unit_gcn.bn.weight = 1e-6: give
+    them trained-like magnitudes so every kernel sees non-trivial operands (same recipe as bench.py)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if k.endswith('gcn1.alpha'):
+                p.fill_(0.7)
+            elif k.endswith('offset_conv.0.weight'):
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            elif k.endswith('gcn1.bn.weight'):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+    return model
+
+
+def fresh_ctrgcn(seed=0, **cfg):
+    import tam_gcn_b200.ctrgcn as C
+    torch.manual_seed(seed)
+    kw = dict(UCLA)
+    kw.update(cfg)
+    return wake_dead_paths(C.Model(**kw), seed)
+
+
+def fresh_stgcn(seed=0, **cfg):
+    import tam_gcn_b200.stgcn as S
+    torch.manual_seed(seed)
+    kw = dict(in_channels=3, num_class=60, num_point=25, num_person=1, graph='graph.ntu_rgb_d.Graph',
+              graph_args=dict(labeling_mode='spatial'))
+    kw.update(cfg)
+    m = S.Model(**kw)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():                                   # edge importance away from exactly 1
+        for p in m.edge_importance:
+            p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+    return m
+
+
+def state_of(model):
+    return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+
+
+def grad_vector(named_grads, keys):
+    return torch.cat([named_grads[k].detach().double().reshape(-1).cpu() for k in keys])

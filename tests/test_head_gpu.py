@@ -1,0 +1,248 @@
+"""The network-end and optimiser kernels (csrc/head.cu) through the C-ABI against their pure-torch emulations and
+against ATen itself: data_bn prologue, pooled classifier, softmax cross-entropy, fused SGD; plus the step engine on
+the GPU: eager step == CUDA-graph replay == the reference loop (oracle + torch.optim.SGD), set_lr on a captured
+graph, warm-up that leaves the training state untouched."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import emu_ops as E
+import helpers as H
+from oracle import gcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch.device('cuda:0')
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(5, 3, 52, 20, 1), (3, 3, 16, 25, 2), (2, 9, 7, 20, 3)])
+@pytest.mark.parametrize('fold', [False, True])
+@pytest.mark.parametrize('train', [True, False])
+def test_data_bn(dt, shape, fold, train):
+    dev = _dev()
+    from tam_gcn_b200 import ops
+    N, C, T, V, M = shape
+    g = torch.Generator(device='cuda').manual_seed(3)
+    x = torch.randn(shape, device=dev, generator=g) * 0.7 + 0.2
+    nch = (1 if fold else M) * V * C
+
+    def make_bn():
+        bn = torch.nn.BatchNorm1d(nch).to(dev).train(train)
+        gg = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            bn.weight.copy_(1 + 0.2 * torch.randn(nch, generator=gg))
+            bn.bias.copy_(0.3 * torch.randn(nch, generator=gg))
+            bn.running_mean.copy_(0.1 * torch.randn(nch, generator=gg))
+            bn.running_var.copy_(0.5 + torch.rand(nch, generator=gg))
+        return bn
+    bn_a, bn_b = make_bn(), make_bn()
+    out_a = torch.empty(N * M, C, T, V, device=dev, dtype=dt)
+    out_b = torch.empty_like(out_a)
+    sv_a = torch.empty(2, nch, device=dev)
+    sv_b = torch.empty(2, nch, device=dev)
+    ops.data_bn_fwd(x, V, fold, bn_a, train, out_a, sv_a[0], sv_a[1])
+    E.data_bn_fwd(x, V, fold, bn_b, train, out_b, sv_b[0], sv_b[1])
+    t = 1e-5 if dt == torch.float32 else 8e-3
+    assert rel(out_a.float(), out_b.float()) < t
+    assert rel(sv_a, sv_b) < 1e-5
+    assert rel(bn_a.running_mean, bn_b.running_mean) < 1e-6 and rel(bn_a.running_var, bn_b.running_var) < 1e-6
+    assert int(bn_a.num_batches_tracked) == int(bn_b.num_batches_tracked) == (1 if train else 0)
+    # backward
+    cot = (torch.randn(out_a.shape, device=dev, generator=g)).to(dt)
+    dg_a, db_a, dx_a = torch.zeros(nch, device=dev), torch.zeros(nch, device=dev), torch.empty(shape, device=dev)
+    dg_b, db_b, dx_b = torch.zeros(nch, device=dev), torch.zeros(nch, device=dev), torch.empty(shape, device=dev)
+    ops.data_bn_bwd(cot, x, V, fold, bn_a.weight, sv_a[0], sv_a[1], train, dg_a, db_a, dx_a)
+    E.data_bn_bwd(cot, x, V, fold, bn_b.weight, sv_b[0], sv_b[1], train, dg_b, db_b, dx_b)
+    assert rel(dg_a, dg_b) < 1e-5 and rel(db_a, db_b) < 1e-5 and rel(dx_a, dx_b) < 2e-5
+    # no input gradient requested
+    ops.data_bn_bwd(cot, x, V, fold, bn_a.weight, sv_a[0], sv_a[1], train, dg_a, db_a, None)
+    assert rel(dg_a, 2 * dg_b) < 1e-5
+
+
+def test_data_bn_three_dim_input_and_aten():
+    """(N, T, V*C) input read through its strides == the reference's view/permute/BatchNorm1d/permute chain."""
+    dev = _dev()
+    from tam_gcn_b200 import functional as Fn
+    N, T, V, C = 4, 11, 20, 3
+    torch.manual_seed(0)
+    x3 = torch.randn(N, T, V * C, device=dev, requires_grad=True)
+    bn = torch.nn.BatchNorm1d(V * C).to(dev).train()
+    ref_bn = copy.deepcopy(bn)
+    out = Fn.DataBnFn.apply(x3, bn, V, False, torch.float32, bn.weight, bn.bias)
+    x = x3.detach().clone().requires_grad_(True)
+    x5 = x.view(N, T, V, -1).permute(0, 3, 1, 2).contiguous().unsqueeze(-1)              # models/ctrgcn.py:325-327
+    r = ref_bn(x5.permute(0, 4, 3, 1, 2).contiguous().view(N, V * C, T))
+    r = r.view(N, 1, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N, C, T, V)
+    cot = torch.randn_like(r)
+    out.backward(cot)
+    r.backward(cot)
+    assert rel(out, r) < 1e-5 and rel(x3.grad, x.grad) < 1e-4
+    assert rel(bn.weight.grad, ref_bn.weight.grad) < 1e-4 and rel(bn.bias.grad, ref_bn.bias.grad) < 1e-4
+    assert rel(bn.running_var, ref_bn.running_var) < 1e-6
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('cfg', [(64, 1, 256, 13, 20, 10), (6, 2, 256, 16, 25, 60), (3, 3, 40, 5, 20, 7)])
+def test_pool_fc_and_cross_entropy(dt, cfg):
+    dev = _dev()
+    from tam_gcn_b200 import ops
+    N, M, C, T, V, K = cfg
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = torch.randn(N * M, C, T, V, device=dev, generator=g).to(dt)
+    W = torch.randn(K, C, device=dev, generator=g) * C ** -0.5
+    b = torch.randn(K, device=dev, generator=g) * 0.1
+    pa, la = torch.empty(N, C, device=dev), torch.empty(N, K, device=dev)
+    pb, lb = torch.empty(N, C, device=dev), torch.empty(N, K, device=dev)
+    ops.pool_fc_fwd(x, M, W, b, pa, la)
+    E.pool_fc_fwd(x, M, W, b, pb, lb)
+    assert rel(pa, pb) < 2e-6 and rel(la, lb) < 1e-5
+    ops.pool_fc_fwd(x, M, None, None, pa, None)
+    assert rel(pa, pb) < 2e-6
+    y = torch.randint(0, K, (N,), device=dev, generator=g)
+    y[N // 2] = -100
+    loss_a, dl_a = torch.empty(1, device=dev), torch.empty(N, K, device=dev)
+    loss_b, dl_b = torch.empty(1, device=dev), torch.empty(N, K, device=dev)
+    ops.softmax_ce_fwd(la, y, loss_a, dl_a)
+    E.softmax_ce_fwd(la, y, loss_b, dl_b)
+    ref = F.cross_entropy(la, y)
+    assert rel(loss_a, loss_b) < 1e-6 and rel(loss_a, ref.reshape(1)) < 1e-6 and rel(dl_a, dl_b) < 1e-5
+    gl = torch.full((1,), 0.37, device=dev)
+    out = torch.empty_like(dl_a)
+    ops.softmax_ce_bwd(dl_a, gl, out)
+    assert rel(out, dl_b * 0.37) < 1e-6
+    ga, dWa, dba = torch.empty_like(x), torch.zeros_like(W), torch.zeros_like(b)
+    gb, dWb, dbb = torch.empty_like(x), torch.zeros_like(W), torch.zeros_like(b)
+    ops.pool_fc_bwd(dl_a, pa, W, M, ga, dWa, dba)
+    E.pool_fc_bwd(dl_a, pb, W, M, gb, dWb, dbb)
+    assert rel(ga.float(), gb.float()) < (1e-5 if dt == torch.float32 else 8e-3)
+    assert rel(dWa, dWb) < 1e-5 and rel(dba, dbb) < 1e-5
+    dp = torch.randn(N, C, device=dev, generator=g)
+    ops.pool_fc_bwd(dp, pa, None, M, ga, None, None)
+    E.pool_fc_bwd(dp, pb, None, M, gb, None, None)
+    assert rel(ga.float(), gb.float()) < (1e-5 if dt == torch.float32 else 8e-3)
+
+
+@pytest.mark.parametrize('n', [1693260 + 3 * 64, 4096, 77])
+@pytest.mark.parametrize('nesterov', [True, False])
+def test_sgd_step_matches_torch_optim(n, nesterov):
+    dev = _dev()
+    from tam_gcn_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(2)
+    P, Mo = torch.randn(n, device=dev, generator=g), torch.zeros(n, device=dev)
+    p_ref = torch.nn.Parameter(P.clone())
+    opt = torch.optim.SGD([p_ref], lr=0.1, momentum=0.9, nesterov=nesterov, weight_decay=1e-4)
+    lr = torch.full((1,), 0.1, device=dev)
+    for it in range(4):
+        G = torch.randn(n, device=dev, generator=g)
+        if it == 3:
+            lr.fill_(0.01)
+            opt.param_groups[0]['lr'] = 0.01
+        p_ref.grad = (G * 0.5).clone()
+        opt.step()
+        ops.sgd_step(P, G, Mo, lr, 0.9, 1e-4, nesterov, grad_scale=0.5)
+        assert rel(P, p_ref.detach()) < 1e-6, it
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# step engine on the GPU
+# --------------------------------------------------------------------------------------------------------------------
+def _fresh_model(seed=0, **kw):
+    return H.fresh_ctrgcn(seed, **kw)
+
+
+def _update_err(a, b, state):
+    num = den = 0.0
+    for k, v in b.items():
+        if v.is_floating_point() and getattr(v, 'requires_grad', False):
+            d_ref = v.detach().double().cpu() - state[k].double()
+            d_a = a[k].detach().double().cpu() - state[k].double()
+            num += float((d_a - d_ref).pow(2).sum())
+            den += float(d_ref.pow(2).sum())
+    return (num / den) ** 0.5
+
+
+def _oracle_steps(state, x, y, V, lrs, dtype):
+    p = O.clone_state(state, dtype, requires_grad=True)
+    opt = torch.optim.SGD([v for v in p.values() if v.requires_grad], lr=lrs[0], momentum=0.9, nesterov=True,
+                          weight_decay=1e-4)
+    losses = []
+    for lr in lrs:
+        opt.param_groups[0]['lr'] = lr
+        opt.zero_grad()
+        loss = F.cross_entropy(O.ctrgcn_forward(x.to(dtype), p, V, train=True), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    return p, losses
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_trainer_steps_match_reference_loop_on_gpu(use_graph):
+    """Three engine steps in fp32 (the last after set_lr) vs the reference loop: oracle forward + torch autograd +
+    torch.optim.SGD (processor/recognition_rgb.py:21-28,48-66).  Criterion: error of the parameter
+    updates against the fp64 oracle <= 3x the error of the fp32 oracle (the reference's own precision).  The graph
+    path must also leave the state untouched by its warm-up: its first replay is step #1."""
+    dev = _dev()
+    import tam_gcn_b200
+    from tam_gcn_b200 import engine
+    m = _fresh_model().to(dev).train()
+    state = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x = O.synthetic_skeletons(8, 52, 20, 1, C=3, seed=3)
+    y = torch.tensor([3, 7, 1, 1, 0, 9, 4, 4])
+    lrs = [1e-4, 1e-4, 1e-5]
+    with tam_gcn_b200.act_dtype(torch.float32):
+        tr = engine.Trainer(m, lr=lrs[0], use_graph=use_graph)
+        losses = []
+        for i, lr in enumerate(lrs):
+            if i == 2:
+                tr.set_lr(lr)
+            losses.append(float(tr.step(x.to(dev), y.to(dev))))
+    ref64, l64 = _oracle_steps(state, x, y, 20, lrs, torch.float64)
+    ref32, l32 = _oracle_steps(state, x, y, 20, lrs, torch.float32)
+    sd = m.state_dict()
+    e_ref, e_our = _update_err(ref32, ref64, state), _update_err(sd, ref64, state)
+    print('graph=%s  update error vs fp64: reference fp32 %.2e, ours %.2e; losses %s vs %s' % (use_graph, e_ref, e_our, losses, l64))
+    assert e_our <= max(3.0 * e_ref, 1e-3), (e_our, e_ref)
+    assert losses[0] == pytest.approx(l64[0], rel=1e-5)
+    for a, b, c in zip(losses, l32, l64):
+        assert abs(a - c) <= max(3.0 * abs(b - c), 2e-3 * abs(c))
+    assert int(sd['data_bn.num_batches_tracked']) == 3 and int(sd['l7.gcn1.bn.num_batches_tracked']) == 3
+    for k in ('l3.tcn1.branches.2.4.running_var', 'data_bn.running_mean', 'l9.gcn1.bn.running_var'):
+        assert O.rel_err(sd[k], ref64[k]) <= max(3.0 * O.rel_err(ref32[k], ref64[k]), 1e-4), k
+
+
+def test_graph_replay_equals_eager_bf16():
+    """bf16 training step: CUDA-graph replay (side stream, direct-to-bucket gradients) == eager, step by step; a
+    batch of another size falls back to the eager path; returned losses do not alias."""
+    dev = _dev()
+    import tam_gcn_b200
+    from tam_gcn_b200 import engine
+    x = O.synthetic_skeletons(8, 52, 20, 1, C=3, seed=5).to(dev)
+    y = torch.tensor([3, 7, 1, 1, 0, 9, 4, 4], device=dev)
+    with tam_gcn_b200.act_dtype(torch.bfloat16):
+        ma, mb = _fresh_model().to(dev).train(), _fresh_model().to(dev).train()
+        ta = engine.Trainer(ma, lr=1e-5, use_graph=True)
+        tb = engine.Trainer(mb, lr=1e-5, use_graph=False, side_stream=False)
+        la, lb = [ta.step(x, y)], [tb.step(x, y)]
+        # same parameters, same batch: the gradient buffers differ only by summation order (atomics, side stream)
+        assert rel(ta.store.G, tb.store.G) < 2e-2
+        la += [ta.step(x, y) for _ in range(2)]
+        lb += [tb.step(x, y) for _ in range(2)]
+        assert la[0].data_ptr() != la[1].data_ptr()
+        assert [float(v) for v in la] == pytest.approx([float(v) for v in lb], rel=2e-2)
+        assert rel(ta.store.P, tb.store.P) < 1e-4
+        small = ta.step(x[:4], y[:4])                          # different shape: eager fallback, still a valid step
+        assert torch.isfinite(small)
+        assert ta.captured_launches > 100

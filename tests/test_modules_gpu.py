@@ -25,12 +25,24 @@ def _cuda():
         pytest.skip('no CUDA device')
 
 
+# Gradient tensors whose fp32 error sits above 1e-4 IN THE REFERENCE ITSELF (reference fp32 vs fp64, SURVEY.md App. D:
+# noise floor 2e-7 ... 7e-5, worst on cancellation-dominated sums): BatchNorm weights behind the max-pool / in front of
+# a second BatchNorm, alpha (a sum of ~1e6 signed terms) and the conv1/conv2 relation weights behind tanh'.
+NOISE_FLOOR = ('.bn.weight', '.1.weight', '.4.weight', 'alpha', '.conv1.weight', '.conv2.weight', '.conv1.bias', '.conv2.bias',
+               'bn.bias', '.1.bias', '.4.bias')
+
+
 @pytest.mark.parametrize('name', MODULE_CASES)
 def test_module_fp32_matches_reference(name):
+    """Module level, fp32: outputs <= 2e-5, input gradient and parameter gradients <= 1e-4 relative to the fp64
+    fixtures, except the documented noise-floor tensors (<= 5e-4)."""
     _cuda()
     res = H.run_case(name, 'cuda')
     rep = []
-    fails = H.compare(name, res, H.load_fixture(name), tol_y=2e-5, tol_dx=1e-4, tol_g=5e-4, tol_buf=1e-5, report=rep)
+    fx = H.load_fixture(name)
+    allow = {k: 5e-4 for k in fx['grads'] if k.endswith(NOISE_FLOOR)}
+    fails = H.compare(name, res, fx, tol_y=2e-5, tol_dx=1e-4, tol_g=1e-4, tol_buf=1e-5, report=rep, tol_gk=allow,
+                      tol_gall=1e-4)
     print(rep[0])
     assert not fails, '\n'.join(fails)
 
@@ -77,12 +89,23 @@ def test_model_fp32_matches_reference(name):
 
 @pytest.mark.parametrize('name', MODEL_CASES)
 def test_model_bf16_close_to_reference(name):
+    """Whole models with bf16 activations on the seeded golden state: logits <= 6e-2 (the state is a chaotic regime:
+    the reference under autocast is at 1.1e-2 ... 1.5e-2), identical top-1 away from near-ties, and GRADIENTS no worse
+    than 2x the reference-under-autocast yard-stick (tests/golden/bf16_yardstick.json) for the input gradient and the
+    kept parameter gradients.  The benchmarked regime (fresh init, batch 64) is graded in test_parity_large_gpu.py."""
     _cuda()
     res = H.run_case(name, 'cuda', torch.bfloat16)
     fx = H.load_fixture(name)
+    ys = _yardstick()[name]
     e = H.O.rel_err(res['y'], fx['y'])
-    print('bf16 %s logits rel err %.3e' % (name, e))
+    e_dx = H.O.rel_err(res['dx'], fx['dx'])
+    ks = [k for k in fx['grads'] if k in res['grads']]
+    ga = torch.cat([res['grads'][k].reshape(-1) for k in ks])
+    gb = torch.cat([fx['grads'][k].reshape(-1) for k in ks])
+    e_g = H.O.rel_err(ga, gb)
+    print('bf16 %s logits %.3e dx %.3e grads %.3e  (yard-stick y %.1e dx %.1e gall %.1e)' % (name, e, e_dx, e_g, ys['y'], ys['dx'], ys['gall']))
     assert e < 6e-2
+    assert e_dx <= max(2.0 * ys['dx'], 5e-2) and e_g <= max(2.0 * ys['gall'], 5e-2)
     # top-1 identical wherever the reference margin is not a near-tie
     top2 = fx['y'].topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 0.05 * fx['y'].abs().max()
