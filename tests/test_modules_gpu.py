@@ -206,3 +206,28 @@ def test_three_dim_input_and_python_alpha():
     x3 = x5[..., 0].permute(0, 2, 3, 1).reshape(x5.shape[0], x5.shape[2], -1)
     with torch.no_grad():
         assert torch.allclose(mm(x3), mm(x5), atol=1e-5, rtol=1e-5)
+
+
+def test_patch_reference_rebinds_module_globals():
+    """`tam_gcn_b200.patch_reference` on a module whose network class looks its layers up as module globals at
+    construction time (what models/ctrgcn.py does; tests/ref_standin.py stands in for it on the GPU box, the real
+    reference is exercised by tests/test_reference_dropin_cpu.py): the foreign Model, with its own ATen prologue / head,
+    runs on the native layers and agrees with tam_gcn_b200.ctrgcn.Model and with the golden fixture."""
+    _cuda()
+    import ref_standin
+    import tam_gcn_b200
+    tam_gcn_b200.patch_reference(ctrgcn_module=ref_standin)
+    import tam_gcn_b200.ctrgcn as C
+    assert ref_standin.TCN_GCN_unit is C.TCN_GCN_unit and ref_standin.CTRGC is C.CTRGC
+    case = H.CASES['ctrgcn_ucla_train']
+    built = H.build_case(case)
+    m = ref_standin.Model(case['A'])
+    m.load_state_dict({k: v.clone() for k, v in built['state'].items()}, strict=True)
+    m = m.cuda().train()
+    x = built['x'].cuda().requires_grad_(True)
+    y = m(x)
+    y.backward(built['cot'].cuda())
+    fx = H.load_fixture('ctrgcn_ucla_train')
+    e_y, e_dx = H.O.rel_err(y, fx['y']), H.O.rel_err(x.grad, fx['dx'])
+    print('patched stand-in Model: y %.2e dx %.2e' % (e_y, e_dx))
+    assert e_y < 1e-4 and e_dx < 2e-2 and (y.argmax(1).cpu() == fx['y'].argmax(1)).all()

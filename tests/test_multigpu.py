@@ -90,3 +90,34 @@ def test_two_gpu_nccl_gradients_and_parameters(use_graph, overlap):
           (e, use_graph, overlap, a['launches']))
     assert e < 2e-3            # fp32 noise floor of end-to-end gradients (2e-3) between two summation orders
     assert not torch.equal(a['P'], a['P0'])
+
+
+def test_data_parallel_two_gpus():
+    """nn.DataParallel — the reference's only multi-GPU mode (processor/io.py:85-87): one process, two devices, replica
+    threads.  Forward + backward in fp32 and bf16 must equal the same model run shard by shard on one device (per-replica
+    BatchNorm statistics), which needs every per-device launch cache of libtamgcn.so to be keyed by device."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 CUDA devices')
+    sys.path.insert(0, HERE)
+    import helpers as H
+    import tam_gcn_b200
+    from oracle import gcn_oracle as O
+    x = O.synthetic_skeletons(8, 52, 20, 1, C=3, seed=6)
+    y = torch.randint(0, 10, (8,), generator=torch.Generator().manual_seed(6))
+    for act, tol in ((torch.float32, 2e-3), (torch.bfloat16, 0.5)):
+        with tam_gcn_b200.act_dtype(act):
+            m = H.fresh_ctrgcn(3).to('cuda:0').train()
+            dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+            out = dp(x.to('cuda:0'))
+            assert out.shape == (8, 10)
+            torch.nn.functional.cross_entropy(out.float(), y.to('cuda:0')).backward()
+            g_dp = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).double().cpu()
+            y_dp = out.detach().double().cpu()
+            ref = H.fresh_ctrgcn(3).to('cuda:0').train()
+            o = torch.cat([ref(x[:4].to('cuda:0')), ref(x[4:].to('cuda:0'))])
+            torch.nn.functional.cross_entropy(o.float(), y.to('cuda:0')).backward()
+            g_ref = torch.cat([p.grad.reshape(-1) for p in ref.parameters()]).double().cpu()
+            e_y = float((y_dp - o.detach().double().cpu()).norm() / o.detach().double().norm())
+            e_g = float((g_dp - g_ref).norm() / g_ref.norm())
+            print('DataParallel %s: logits %.2e grads %.2e' % (act, e_y, e_g))
+            assert e_y < (1e-5 if act == torch.float32 else 3e-2) and e_g < tol
