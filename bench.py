@@ -511,7 +511,7 @@ def main():
             for b in bns:
                 b.momentum = 0.1
             model.eval()
-        runner = engine.Predictor(model, use_graph=not args.no_graph)
+        runner = engine.Predictor(model, use_graph=not args.no_graph, eval_mode=w['family'] != 'fusion')
         out0 = runner(x)
         with ops.account(acct), torch.no_grad():
             model(x)

@@ -202,13 +202,20 @@ int tamgcn_data_bn_bwd(int dtype, const void* g, const float* x, const int64_t* 
                        int M, int fold_m, const float* gamma, const float* mean, const float* invstd, int train,
                        float* dgamma, float* dbeta, float* dx, tamgcn_stream stream);
 /* Model.forward head, models/ctrgcn.py:343-348 / models/stgcn.py:187-195: pooled[n,c] = mean over persons and (T*V) of
- * x[(n*M+m), c, :]; logits = pooled W^T + b (W (K,C), b (K) or NULL; W == NULL: pooling only).  pooled (N,C), logits (N,K) fp32. */
-int tamgcn_pool_fc_fwd(int dtype, const void* x, int N, int M, int C, int TV, int K, const float* W, const float* b,
-                       float* pooled, float* logits, tamgcn_stream stream);
-/* g[(n*M+m), c, :] = (sum_k dlogits[n,k] W[k,c]) / (M*TV)  (NULL to skip);  dW[k,c] += dlogits[n,k]*pooled[n,c];
- * db[k] += dlogits[n,k]  (NULL to skip).  W == NULL (pooling only, K == C): dlogits is the cotangent of pooled. */
-int tamgcn_pool_fc_bwd(int dtype, const float* dlogits, const float* pooled, const float* W, int N, int M, int C, int TV,
-                       int K, void* g, float* dW, float* db, tamgcn_stream stream);
+ * x[(n*M+m), c, :]; logits = (gate .* pooled) W^T + b (W (K,C), b (K) or NULL; W == NULL: pooling only).  pooled (N,C)
+ * (always the RAW mean), logits (N,K) fp32.  gate (N,C) or NULL: the channel attention of the cross-modal head,
+ * models/resnet_gcn_attention.py:108-118 — f_rgb * att -> AdaptiveAvgPool2d -> classifier == classifier(att .* mean(f_rgb)). */
+int tamgcn_pool_fc_fwd(int dtype, const void* x, int N, int M, int C, int TV, int K, const float* gate, const float* W,
+                       const float* b, float* pooled, float* logits, tamgcn_stream stream);
+/* with d = sum_k dlogits[n,k] W[k,c]:  g[(n*M+m), c, :] = d * gate[n,c] / (M*TV)  (NULL to skip);
+ * dW[k,c] += dlogits[n,k]*gate[n,c]*pooled[n,c];  db[k] += dlogits[n,k];  dgate[n,c] = d * pooled[n,c]  (each NULL to
+ * skip).  W == NULL (pooling only, K == C): dlogits is the cotangent of pooled. */
+int tamgcn_pool_fc_bwd(int dtype, const float* dlogits, const float* pooled, const float* gate, const float* W, int N,
+                       int M, int C, int TV, int K, void* g, float* dW, float* db, float* dgate, tamgcn_stream stream);
+/* out (C,R) = f(in (R,C))^T, fp32.  mode 0: f = identity; 1: f = sigmoid; 2: f = in * aux * (1 - aux) with aux (R,C) the
+ * sigmoid output (backward of mode 1).  Glue of the attention MLP of models/resnet_gcn_attention.py:59-65, which runs on
+ * the convolution kernels with the batch as the position axis. */
+int tamgcn_transpose_act(const float* in, const float* aux, int R, int C, int mode, float* out, tamgcn_stream stream);
 /* nn.CrossEntropyLoss (mean over the samples whose label is in [0,K); other labels, e.g. -100, are ignored),
  * processor/recognition_rgb.py:19,61.  loss: one float; dlogits (N,K) = d loss / d logits (NULL to skip). */
 int tamgcn_softmax_ce_fwd(const float* logits, const int64_t* labels, int N, int K, float* loss, float* dlogits,

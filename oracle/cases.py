@@ -63,6 +63,12 @@ CASES = {
     'st_gcn_3_64_nores': case('st_gcn', cin=3, cout=64, K=3, stride=1, residual=False, T=20, seed=24),
     'stgcn_ntu_train': dict(case('stgcn_model', graph='graph.ntu_rgb_d.Graph', N=2, T=32, seed=25, num_class=60, num_point=25),
                             store_grads=False, keep_grads=('edge_importance.3', 'fcn.weight', 'st_gcn_networks.4.residual.0.weight')),
+    # cross-modal fusion head (models/resnet_gcn_attention.py): frozen CTR-GCN -> attention gate -> gated pool -> classifier;
+    # the backbone output f_rgb is an input of the case (the ResNet itself is outside the hot path)
+    'fusion_ucla_train': dict(case('fusion_model', N=4, T=52, seed=26, num_class=10, num_point=20, num_person=1,
+                                   graph='graph.ucla.Graph'), store_grads=False,
+                              keep_grads=('attention_transform.0.bias', 'attention_transform.1.weight', 'classifier.weight',
+                                          'attention_transform.3.bias')),
 }
 for _c in CASES.values():
     _c['args'].setdefault('graph', _c['graph'])
@@ -122,6 +128,12 @@ def build_case(c):
     elif kind == 'stgcn_model':
         p = O.make_stgcn_state(A, a['num_class'], seed=seed, dtype=torch.float64)
         xs, ys = (N, 3, T, V, 2), (N, a['num_class'])
+    elif kind == 'fusion_model':
+        pg = O.make_ctrgcn_state(A, a['num_class'], a['num_person'], seed=seed, dtype=torch.float64)
+        p = {'gcn.' + k: v for k, v in pg.items()}
+        O.add_fusion_head(p, g, a['num_class'])
+        extra['f_rgb'] = torch.relu(torch.randn(N, 2048, 7, 7, generator=g))
+        xs, ys = (N, 3, T, V, a['num_person']), (N, a['num_class'])
     else:
         raise KeyError(kind)
     state = O.cast_state(p, torch.float32)          # fp32-representable values, shared by all precisions
@@ -155,4 +167,6 @@ def oracle_forward(c, x, p, extra):
         return O.st_gcn_block(x, extra['A'], p, 'm', a['stride'], a['residual'], train=train)
     if kind == 'stgcn_model':
         return O.stgcn_forward(x, p, V, train)
+    if kind == 'fusion_model':
+        return O.fusion_forward(x, extra['f_rgb'], p, V, train)
     raise KeyError(kind)

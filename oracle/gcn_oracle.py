@@ -219,6 +219,37 @@ def stgcn_forward(x, p, num_point, train=True):
 
 
 # --------------------------------------------------------------------------------------
+# cross-modal fusion head  (models/resnet_gcn_attention.py)
+# --------------------------------------------------------------------------------------
+def fusion_attention(x_gcn, p, num_point, train=True):
+    """GCN branch of ResNet_GCN_Attention.forward, models/resnet_gcn_attention.py:82-89: CTR-GCN feature, mean over
+    (T, V, M), attention_transform = Linear -> BatchNorm1d -> ReLU -> Linear -> Sigmoid (:59-65).  -> (N, 2048)."""
+    pg = {k[4:]: v for k, v in p.items() if k.startswith('gcn.')}
+    f = ctrgcn_extract_feature(x_gcn, pg, num_point, train).mean(dim=(2, 3, 4))
+    h = F.linear(f, p['attention_transform.0.weight'], p['attention_transform.0.bias'])
+    h = torch.relu(batch_norm(h, p, 'attention_transform.1', train))
+    return torch.sigmoid(F.linear(h, p['attention_transform.3.weight'], p['attention_transform.3.bias']))
+
+
+def fusion_forward(x_gcn, f_rgb, p, num_point, train=True):
+    """ResNet_GCN_Attention.forward from the backbone output f_rgb (N, 2048, 7, 7) on, :108-120: channel gate,
+    global average pool, classifier."""
+    att = fusion_attention(x_gcn, p, num_point, train)
+    out = (f_rgb * att.unsqueeze(-1).unsqueeze(-1)).mean((2, 3))
+    return F.linear(out, p['classifier.weight'], p['classifier.bias'])
+
+
+def add_fusion_head(p, g, num_class=10, cg=256, cr=2048):
+    def lin(pre, co, ci):
+        p[pre + '.weight'] = torch.randn(co, ci, generator=g, dtype=torch.float64) * ci ** -0.5
+        p[pre + '.bias'] = 0.1 * torch.randn(co, generator=g, dtype=torch.float64)
+    lin('attention_transform.0', cr // 2, cg)
+    _add_bn(p, 'attention_transform.1', cr // 2, g)
+    lin('attention_transform.3', cr, cr // 2)
+    lin('classifier', num_class, cr)
+
+
+# --------------------------------------------------------------------------------------
 # synthetic state (reference-named parameter dicts) and inputs  (SURVEY.md §8d)
 # --------------------------------------------------------------------------------------
 def _kaiming_fan_out(shape, g):

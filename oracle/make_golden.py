@@ -63,10 +63,27 @@ def ref_module(case, state):
     elif kind == 'stgcn_model':
         m = RS.Model(in_channels=3, num_class=a['num_class'], num_point=a['num_point'], num_person=1,
                      graph=a['graph'], graph_args=dict(labeling_mode='spatial'))
+    elif kind == 'fusion_model':
+        # the reference asks torch.hub for ImageNet weights (models/resnet_gcn_attention.py:32): no network here, and the
+        # backbone is outside the hot path — build it unpretrained and replace its stages by identities so that the
+        # UNMODIFIED forward (:82-120) runs the head on the f_rgb the case supplies as `x_rgb`
+        import models.resnet as RR
+        import models.resnet_gcn_attention as RF
+        real = RR.resnet50
+        RF.resnet50 = lambda pretrained=True: real(pretrained=False)
+        try:
+            m = RF.ResNet_GCN_Attention(num_class=a['num_class'], num_point=a['num_point'], num_person=a['num_person'],
+                                        graph=a['graph'], graph_args=dict(labeling_mode='spatial'), in_channels_rgb=3)
+        finally:
+            RF.resnet50 = real
+        r = torch.nn.Module()
+        for nm in ('conv1', 'bn1', 'relu', 'maxpool', 'layer1', 'layer2', 'layer3', 'layer4'):
+            setattr(r, nm, torch.nn.Identity())
+        m.resnet = r
     else:
         raise KeyError(kind)
     m = m.double()
-    sd = strip(state, 'm') if kind not in ('ctrgcn_model', 'stgcn_model') else state
+    sd = strip(state, 'm') if not kind.endswith('_model') else state
     sd = {k: v for k, v in sd.items() if not k.startswith('__')}
     missing, unexpected = m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
     assert not missing and not unexpected
@@ -81,13 +98,18 @@ def ref_forward(case, m, x, extra):
         return m(x, extra['A'])[0]
     if kind == 'st_gcn':
         return m(x, extra['A'])[0]
+    if kind == 'fusion_model':
+        return m(x, extra['f_rgb'])
     return m(x)
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     worst = 0.0
+    only = [a for a in sys.argv[1:] if not a.startswith('-')]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         built = build_case(case)
         state64 = O.clone_state(built['state'], D)
         m = ref_module(case, state64)
@@ -135,7 +157,9 @@ def main():
         fx = {'case': name,
               'state_checksum': float(sum(v.double().abs().sum() for v in built['state'].values()
                                           if torch.is_tensor(v) and v.is_floating_point())),
-              'x': built['x'], 'cot': built['cot'], 'extra': built['extra'],
+              'x': built['x'], 'cot': built['cot'],
+              # the 1.6 MB backbone feature map of the fusion case is regenerated from the seed, not stored
+              'extra': {} if case['kind'] == 'fusion_model' else built['extra'],
               'y': ref['y'].float(), 'dx': ref['dx'].float()}
         if case.get('store_grads', True):
             fx['grads'] = {k: v.float() for k, v in grads.items()}

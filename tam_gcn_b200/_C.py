@@ -67,8 +67,9 @@ SIGNATURES = {
     'tamgcn_data_bn_fwd': [i32, vp, C.POINTER(i64), i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp,
                            vp, vp],
     'tamgcn_data_bn_bwd': [i32, vp, vp, C.POINTER(i64), i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp],
-    'tamgcn_pool_fc_fwd': [i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
-    'tamgcn_pool_fc_bwd': [i32, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp],
+    'tamgcn_pool_fc_fwd': [i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
+    'tamgcn_pool_fc_bwd': [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+    'tamgcn_transpose_act': [vp, vp, i32, i32, i32, vp, vp],
     'tamgcn_softmax_ce_fwd': [vp, vp, i32, i32, vp, vp, vp],
     'tamgcn_softmax_ce_bwd': [vp, vp, i32, i32, vp, vp],
     'tamgcn_sgd_step': [vp, vp, vp, i64, vp, f32, f32, i32, f32, vp],

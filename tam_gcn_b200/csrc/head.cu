@@ -148,8 +148,9 @@ data_bn_bwd_kernel(DataBnP p, const T* __restrict__ g, const float* __restrict__
 // (x.view(N,M,C,-1).mean(3).mean(1) == mean over all M*TV elements since every person has the same TV)
 template <typename T>
 __global__ void __launch_bounds__(256)
-pool_fc_fwd_kernel(int N, int M, int C, int TV, int K, const T* __restrict__ x, const float* __restrict__ W,
-                   const float* __restrict__ b, float* __restrict__ pooled, float* __restrict__ logits) {
+pool_fc_fwd_kernel(int N, int M, int C, int TV, int K, const T* __restrict__ x, const float* __restrict__ gate,
+                   const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ pooled,
+                   float* __restrict__ logits) {
     extern __shared__ float sp[];                       // C floats
     const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float inv = 1.f / (float)(M * TV);
@@ -160,7 +161,10 @@ pool_fc_fwd_kernel(int N, int M, int C, int TV, int K, const T* __restrict__ x, 
             for (int e = lane; e < TV; e += 32) s += ldf<T>(px + e);
         }
         s = warp_sum(s) * inv;
-        if (lane == 0) { sp[c] = s; pooled[(long long)n * C + c] = s; }
+        if (lane == 0) {
+            pooled[(long long)n * C + c] = s;                       // the raw mean is what the backward needs
+            sp[c] = gate ? s * __ldg(gate + (long long)n * C + c) : s;
+        }
     }
     __syncthreads();
     if (!W) return;
@@ -177,7 +181,8 @@ pool_fc_fwd_kernel(int N, int M, int C, int TV, int K, const T* __restrict__ x, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 pool_fc_bwd_kernel(int N, int M, int C, int TV, int K, const float* __restrict__ dl, const float* __restrict__ pooled,
-                   const float* __restrict__ W, T* __restrict__ g, float* dW, float* db) {
+                   const float* __restrict__ gate, const float* __restrict__ W, T* __restrict__ g, float* dW, float* db,
+                   float* __restrict__ dgate) {
     extern __shared__ float sm[];                       // K floats dl, C floats dpooled
     float* sdl = sm;
     float* sdp = sm + K;
@@ -191,16 +196,19 @@ pool_fc_bwd_kernel(int N, int M, int C, int TV, int K, const float* __restrict__
     const float inv = 1.f / (float)(M * TV);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
+        const float gt = gate ? __ldg(gate + (long long)n * C + c) : 1.f;
         if (W) {
-            const float pc = __ldg(pooled + (long long)n * C + c);
+            const float mean = __ldg(pooled + (long long)n * C + c);
+            const float pc = mean * gt;
             for (int k = 0; k < K; ++k) {
                 s = fmaf(sdl[k], __ldg(W + (long long)k * C + c), s);
                 if (dW) atomicAdd(dW + (long long)k * C + c, sdl[k] * pc);
             }
+            if (dgate) dgate[(long long)n * C + c] = s * mean;
         } else {
             s = sdl[c];                                 // pooling only: dlogits IS the cotangent of pooled (K == C)
         }
-        sdp[c] = s * inv;
+        sdp[c] = s * gt * inv;
     }
     __syncthreads();
     if (!g) return;
@@ -264,6 +272,32 @@ scale_by_scalar_kernel(long long n, const float* __restrict__ a, const float* __
     const float k = __ldg(s);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = a[i] * k;
+}
+
+// ---- (R, C) -> (C, R) transpose of a small fp32 matrix with an optional activation ------------------------------------
+// mode 0: out = in^T;  1: out = sigmoid(in)^T;  2: out = (in * aux * (1 - aux))^T  (aux = the sigmoid output, (R, C):
+// backward of mode 1 for a cotangent `in` of the TRANSPOSED result, i.e. in and aux are both (R, C))
+__global__ void __launch_bounds__(256)
+transpose_act_kernel(int R, int C, int mode, const float* __restrict__ in, const float* __restrict__ aux,
+                     float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + tx;
+        float v = 0.f;
+        if (r < R && c < C) {
+            v = __ldg(in + (long long)r * C + c);
+            if (mode == 1) v = 1.f / (1.f + expf(-v));
+            else if (mode == 2) { const float a = __ldg(aux + (long long)r * C + c); v = v * a * (1.f - a); }
+        }
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + tx;
+        if (r < R && c < C) out[(long long)c * R + r] = tile[tx][j];
+    }
 }
 
 // ---- SGD (momentum, nesterov, weight decay) over flat buffers -------------------------------------------------------
@@ -348,8 +382,8 @@ extern "C" int tamgcn_data_bn_bwd(int dtype, const void* g, const float* x, cons
     return check_launch("data_bn_bwd");
 }
 
-extern "C" int tamgcn_pool_fc_fwd(int dtype, const void* x, int N, int M, int C, int TV, int K, const float* W,
-                                  const float* b, float* pooled, float* logits, tamgcn_stream stream) {
+extern "C" int tamgcn_pool_fc_fwd(int dtype, const void* x, int N, int M, int C, int TV, int K, const float* gate,
+                                  const float* W, const float* b, float* pooled, float* logits, tamgcn_stream stream) {
     TG_REQUIRE(N > 0 && M > 0 && C > 0 && TV > 0, "pool_fc_fwd: empty shape N=%d M=%d C=%d TV=%d", N, M, C, TV);
     TG_REQUIRE(x && pooled, "pool_fc_fwd: null tensor");
     TG_REQUIRE(!W || (K > 0 && logits), "pool_fc_fwd: linear layer needs K > 0 and a logits buffer");
@@ -357,24 +391,25 @@ extern "C" int tamgcn_pool_fc_fwd(int dtype, const void* x, int N, int M, int C,
     TG_REQUIRE(dtype == TAMGCN_F32 || dtype == TAMGCN_BF16, "pool_fc_fwd: bad dtype %d", dtype);
     const size_t sm = C * sizeof(float);
     if (dtype == TAMGCN_F32)
-        pool_fc_fwd_kernel<float><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, (const float*)x, W, b, pooled, logits);
+        pool_fc_fwd_kernel<float><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, (const float*)x, gate, W, b, pooled, logits);
     else
-        pool_fc_fwd_kernel<bf16><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, (const bf16*)x, W, b, pooled, logits);
+        pool_fc_fwd_kernel<bf16><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, (const bf16*)x, gate, W, b, pooled, logits);
     count_launch();
     return check_launch("pool_fc_fwd");
 }
 
-extern "C" int tamgcn_pool_fc_bwd(int dtype, const float* dlogits, const float* pooled, const float* W, int N, int M,
-                                  int C, int TV, int K, void* g, float* dW, float* db, tamgcn_stream stream) {
+extern "C" int tamgcn_pool_fc_bwd(int dtype, const float* dlogits, const float* pooled, const float* gate, const float* W,
+                                  int N, int M, int C, int TV, int K, void* g, float* dW, float* db, float* dgate,
+                                  tamgcn_stream stream) {
     TG_REQUIRE(N > 0 && M > 0 && C > 0 && TV > 0 && K > 0, "pool_fc_bwd: empty shape");
-    TG_REQUIRE(dlogits && (W ? pooled != nullptr : (K == C && !dW && !db)), "pool_fc_bwd: null tensor / pooling-only needs K == C");
+    TG_REQUIRE(dlogits && (W ? pooled != nullptr : (K == C && !dW && !db && !dgate)), "pool_fc_bwd: null tensor / pooling-only needs K == C");
     TG_REQUIRE((size_t)(C + K) * sizeof(float) <= 48 * 1024, "pool_fc_bwd: C+K too large");
     TG_REQUIRE(dtype == TAMGCN_F32 || dtype == TAMGCN_BF16, "pool_fc_bwd: bad dtype %d", dtype);
     const size_t sm = (size_t)(C + K) * sizeof(float);
     if (dtype == TAMGCN_F32)
-        pool_fc_bwd_kernel<float><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, W, (float*)g, dW, db);
+        pool_fc_bwd_kernel<float><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, gate, W, (float*)g, dW, db, dgate);
     else
-        pool_fc_bwd_kernel<bf16><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, W, (bf16*)g, dW, db);
+        pool_fc_bwd_kernel<bf16><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, gate, W, (bf16*)g, dW, db, dgate);
     count_launch();
     return check_launch("pool_fc_bwd");
 }
@@ -396,6 +431,16 @@ extern "C" int tamgcn_softmax_ce_bwd(const float* dl_saved, const float* gloss, 
     scale_by_scalar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, dl_saved, gloss, dlogits);
     count_launch();
     return check_launch("softmax_ce_bwd");
+}
+
+extern "C" int tamgcn_transpose_act(const float* in, const float* aux, int R, int C, int mode, float* out,
+                                    tamgcn_stream stream) {
+    TG_REQUIRE(R > 0 && C > 0 && in && out && mode >= 0 && mode <= 2 && (mode != 2 || aux), "transpose_act: bad arguments");
+    dim3 grid((C + 31) / 32, (R + 31) / 32);
+    TG_REQUIRE(grid.y <= 65535, "transpose_act: too many rows");
+    transpose_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(R, C, mode, in, aux, out);
+    count_launch();
+    return check_launch("transpose_act");
 }
 
 extern "C" int tamgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, const float* lr,

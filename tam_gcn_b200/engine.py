@@ -218,8 +218,10 @@ class Trainer:
 class Predictor:
     """Inference (eval-mode forward) as a CUDA graph, for the large-batch throughput sweep."""
 
-    def __init__(self, model, use_graph=True):
-        self.model = model.eval()
+    def __init__(self, model, use_graph=True, eval_mode=True):
+        """eval_mode=False keeps the model in train() — the frozen-but-training GCN branch of the cross-modal fusion
+        model (models/resnet_gcn_attention.py:24-26): forward only, batch statistics, running stats updated."""
+        self.model = model.eval() if eval_mode else model.train()
         self.use_graph = use_graph
         self.graph = None
         self.static_x = self.static_out = None

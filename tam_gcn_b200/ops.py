@@ -504,17 +504,18 @@ def data_bn_bwd(g, x, num_point, fold_m, gamma, mean, invstd, train, dgamma, dbe
     _count('head+sgd', 4 * x.numel() + g.element_size() * g.numel() + (4 * x.numel() if dx is not None else 0))
 
 
-def pool_fc_fwd(x, M, W, b, pooled, logits):
-    """x: (N*M, C, T, V); pooled (N, C) fp32; logits (N, K) fp32 (W None: pooling only)."""
+def pool_fc_fwd(x, M, W, b, pooled, logits, gate=None):
+    """x: (N*M, C, T, V); pooled (N, C) fp32 (raw mean); logits (N, K) fp32 = (gate .* pooled) W^T + b (W None: pooling only)."""
     NM, Cc, T, V = x.shape
     N = NM // M
     K = W.shape[0] if W is not None else 0
-    _C.check(_C.lib().tamgcn_pool_fc_fwd(_dt(x), _full(x, x.dtype), N, M, Cc, T * V, K, _f32(W, K * Cc if W is not None else None),
-                                         _f32(b), _f32(pooled, N * Cc), _f32(logits), _stream()), 'tamgcn_pool_fc_fwd')
+    _C.check(_C.lib().tamgcn_pool_fc_fwd(_dt(x), _full(x, x.dtype), N, M, Cc, T * V, K, _f32(gate, N * Cc if gate is not None else None),
+                                         _f32(W, K * Cc if W is not None else None), _f32(b), _f32(pooled, N * Cc),
+                                         _f32(logits), _stream()), 'tamgcn_pool_fc_fwd')
     _count('head+sgd', x.element_size() * x.numel())
 
 
-def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db):
+def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db, gate=None, dgate=None):
     """W None: pooling only (dlogits is the cotangent of pooled, K == C)."""
     N, K = dlogits.shape
     Cc = pooled.shape[1]
@@ -523,10 +524,17 @@ def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db):
         dt = _dt(g)
     else:
         TV, dt = 1, _C.F32
-    _C.check(_C.lib().tamgcn_pool_fc_bwd(dt, _f32(dlogits), _f32(pooled), _f32(W, K * Cc if W is not None else None), N, M, Cc, TV, K,
-                                         None if g is None else _full(g, g.dtype), _f32(dW), _f32(db), _stream()),
-             'tamgcn_pool_fc_bwd')
+    _C.check(_C.lib().tamgcn_pool_fc_bwd(dt, _f32(dlogits), _f32(pooled), _f32(gate), _f32(W, K * Cc if W is not None else None),
+                                         N, M, Cc, TV, K, None if g is None else _full(g, g.dtype), _f32(dW), _f32(db),
+                                         _f32(dgate), _stream()), 'tamgcn_pool_fc_bwd')
     _count('head+sgd', g.element_size() * g.numel() if g is not None else 0)
+
+
+def transpose_act(inp, out, mode=0, aux=None):
+    """out (C, R) = f(inp (R, C))^T;  mode 0 identity, 1 sigmoid, 2 sigmoid backward (inp * aux * (1 - aux))."""
+    R, Cc = inp.shape
+    _C.check(_C.lib().tamgcn_transpose_act(_f32(inp), _f32(aux, R * Cc if aux is not None else None), R, Cc, mode,
+                                           _f32(out, R * Cc), _stream()), 'tamgcn_transpose_act')
 
 
 def softmax_ce_fwd(logits, labels, loss, dl):

@@ -332,23 +332,35 @@ def data_bn_bwd(g, x, num_point, fold_m, gamma, mean, invstd, train, dgamma, dbe
         dx.copy_(d.float())
 
 
-def pool_fc_fwd(x, M, W, b, pooled, logits):
+def pool_fc_fwd(x, M, W, b, pooled, logits, gate=None):
     NM, C, T, V = x.shape
     p = x.float().reshape(NM // M, M, C, T * V).mean(3).mean(1)
     pooled.copy_(p)
     if W is not None:
-        logits.copy_(F.linear(p, W, b))
+        logits.copy_(F.linear(p if gate is None else p * gate, W, b))
 
 
-def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db):
+def pool_fc_bwd(dlogits, pooled, W, M, g, dW, db, gate=None, dgate=None):
     dp = dlogits if W is None else dlogits @ W
+    gt = 1.0 if gate is None else gate
     if dW is not None:
-        dW += dlogits.t() @ pooled
+        dW += dlogits.t() @ (pooled * gt)
     if db is not None:
         db += dlogits.sum(0)
+    if dgate is not None:
+        dgate.copy_(dp * pooled)
     if g is not None:
         NM, C, T, V = g.shape
-        g.copy_((dp / (M * T * V)).view(NM // M, 1, C, 1, 1).expand(NM // M, M, C, T, V).reshape(g.shape).to(g.dtype))
+        g.copy_((dp * gt / (M * T * V)).view(NM // M, 1, C, 1, 1).expand(NM // M, M, C, T, V).reshape(g.shape).to(g.dtype))
+
+
+def transpose_act(inp, out, mode=0, aux=None):
+    v = inp
+    if mode == 1:
+        v = torch.sigmoid(inp)
+    elif mode == 2:
+        v = inp * aux * (1 - aux)
+    out.copy_(v.t())
 
 
 def softmax_ce_fwd(logits, labels, loss, dl):
@@ -378,7 +390,7 @@ def sgd_step(P, G, Mo, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
 ALL = ['conv_pack_weights', 'conv_fwd', 'conv_dgrad', 'conv_wgrad', 'mean_t', 'ctrgc_fwd', 'ctrgc_bwd', 'bn_finalize', 'bn_bwd_coef',
        'gcn_epilogue_fwd', 'gcn_epilogue_bwd', 'gcn_mid_bwd', 'tcn_epilogue_fwd', 'tcn_epilogue_bwd', 'maxpool_fwd',
        'maxpool_bwd', 'graph_agg_fwd', 'graph_agg_bwd', 'data_bn_fwd', 'data_bn_bwd', 'pool_fc_fwd', 'pool_fc_bwd',
-       'softmax_ce_fwd', 'softmax_ce_bwd', 'sgd_step']
+       'softmax_ce_fwd', 'softmax_ce_bwd', 'sgd_step', 'transpose_act']
 
 
 def install(monkeypatch=None):

@@ -45,7 +45,21 @@ def our_module(case):
     if kind == 'stgcn_model':
         return S.Model(in_channels=3, num_class=a['num_class'], num_point=a['num_point'], num_person=1,
                        graph=a['graph'], graph_args=dict(labeling_mode='spatial'))
+    if kind == 'fusion_model':
+        import tam_gcn_b200.fusion as Fu
+        return Fu.ResNet_GCN_Attention(num_class=a['num_class'], num_point=a['num_point'], num_person=a['num_person'],
+                                       graph=a['graph'], graph_args=dict(labeling_mode='spatial'), in_channels_rgb=3,
+                                       resnet=identity_backbone())
     raise KeyError(kind)
+
+
+def identity_backbone():
+    """Stand-in for the ResNet-50 of the fusion model (outside the hot path): every stage is the identity, so the
+    `x_rgb` argument IS the (N, 2048, 7, 7) backbone output the head consumes."""
+    r = torch.nn.Module()
+    for nm in ('conv1', 'bn1', 'relu', 'maxpool', 'layer1', 'layer2', 'layer3', 'layer4'):
+        setattr(r, nm, torch.nn.Identity())
+    return r
 
 
 def load_state(m, case, state):
@@ -62,6 +76,8 @@ def run_module(case, m, x, extra):
         return m(x, extra['A'], extra['alpha'])
     if kind in ('ctg', 'st_gcn'):
         return m(x, extra['A'])[0]
+    if kind == 'fusion_model':
+        return m(x, extra['f_rgb'])
     return m(x)
 
 
