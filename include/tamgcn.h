@@ -230,6 +230,15 @@ int tamgcn_softmax_ce_bwd(const float* dl_saved, const float* gloss, int N, int 
 int tamgcn_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, const float* lr, float momentum,
                     float weight_decay, int nesterov, float grad_scale, tamgcn_stream stream);
 
+/* ---- GPU-side skeleton feeder: feeder/feeder_nucla_gcn.py:85-130 for a whole batch --------------- */
+/* raw: (S, Lmax, V, 3) fp32 padded skeleton sequences resident on the device, length[S] their frame counts.  For batch
+ * element b: sample[b] selects the sequence, view[b] = (agx degrees, agy degrees, scale) the random view transform
+ * (0, 0, 1 for evaluation), frame_idx[b, T] the (sorted) frames to keep.  mode 0 joint / 1 bone (bone_parent[V]: for
+ * joint a the 0-based joint b subtracted from it, -1 -> zero) / 2 motion.  out: (B, 3, T, V, 1) fp32 in [-1, 1]. */
+int tamgcn_feeder_nucla(const float* raw, const int32_t* length, const int64_t* sample, const float* view,
+                        const int32_t* frame_idx, const int32_t* bone_parent, int B, int Lmax, int V, int T, int mode,
+                        float* out, tamgcn_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

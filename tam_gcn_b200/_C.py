@@ -73,6 +73,7 @@ SIGNATURES = {
     'tamgcn_softmax_ce_fwd': [vp, vp, i32, i32, vp, vp, vp],
     'tamgcn_softmax_ce_bwd': [vp, vp, i32, i32, vp, vp],
     'tamgcn_sgd_step': [vp, vp, vp, i64, vp, f32, f32, i32, f32, vp],
+    'tamgcn_feeder_nucla': [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp],
 }
 
 _lib = None

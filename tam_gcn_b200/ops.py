@@ -557,3 +557,19 @@ def sgd_step(P, G, Mo, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
                                       float(weight_decay), 1 if nesterov else 0, float(grad_scale), _stream()),
              'tamgcn_sgd_step')
     _count('head+sgd', 20 * n)
+
+
+def feeder_nucla(raw, length, sample, view, frame_idx, bone_parent, mode, out):
+    """GPU feeder (csrc/feeder.cu).  raw (S, Lmax, V, 3) fp32, length (S) int32, sample (B) int64, view (B, 3) fp32,
+    frame_idx (B, T) int32, bone_parent (V) int32 or None, out (B, 3, T, V, 1) fp32."""
+    S, Lmax, V, _ = raw.shape
+    B, T = frame_idx.shape
+    for t, dt in ((raw, torch.float32), (length, torch.int32), (sample, torch.int64), (view, torch.float32),
+                  (frame_idx, torch.int32), (out, torch.float32)):
+        if t.dtype != dt or not t.is_contiguous() or not t.is_cuda:
+            raise TypeError('feeder_nucla: expected contiguous CUDA %s tensors' % dt)
+    if out.shape != (B, 3, T, V, 1) or view.shape != (B, 3) or sample.shape != (B,):
+        raise ValueError('feeder_nucla: shape mismatch')
+    _C.check(_C.lib().tamgcn_feeder_nucla(raw.data_ptr(), length.data_ptr(), sample.data_ptr(), view.data_ptr(),
+                                          frame_idx.data_ptr(), _p(bone_parent), B, Lmax, V, T, int(mode), out.data_ptr(),
+                                          _stream()), 'tamgcn_feeder_nucla')

@@ -387,10 +387,34 @@ def sgd_step(P, G, Mo, lr, momentum, weight_decay, nesterov, grad_scale=1.0):
         P.sub_(float(lr) * (g + momentum * Mo if nesterov else Mo))
 
 
+def feeder_nucla(raw, length, sample, view, frame_idx, bone_parent, mode, out):
+    import math
+    B, T = frame_idx.shape
+    V = raw.shape[2]
+    for b in range(B):
+        s = int(sample[b])
+        L = int(length[s])
+        val = raw[s, :L].double()
+        val = val - val[0, 1]
+        ax, ay, sc = math.radians(float(view[b, 0])), math.radians(float(view[b, 1])), float(view[b, 2])
+        Rx = torch.tensor([[1, 0, 0], [0, math.cos(ax), math.sin(ax)], [0, -math.sin(ax), math.cos(ax)]], dtype=torch.float64)
+        Ry = torch.tensor([[math.cos(ay), 0, -math.sin(ay)], [0, 1, 0], [math.sin(ay), 0, math.cos(ay)]], dtype=torch.float64)
+        X = val.reshape(-1, 3) @ (Ry @ Rx * sc).to(val.device)
+        lo, hi = X.min(0).values, X.max(0).values
+        X = ((X - lo) / (hi - lo + 1e-6) * 2 - 1).reshape(L, V, 3)
+        d = X[frame_idx[b].long()]
+        if mode == 1:
+            par = bone_parent.long()
+            d = torch.where((par >= 0)[None, :, None], d - d[:, par.clamp_min(0)], torch.zeros_like(d))
+        elif mode == 2:
+            d = torch.cat([d[1:] - d[:-1], torch.zeros_like(d[:1])])
+        out[b] = d.permute(2, 0, 1).unsqueeze(-1).float()
+
+
 ALL = ['conv_pack_weights', 'conv_fwd', 'conv_dgrad', 'conv_wgrad', 'mean_t', 'ctrgc_fwd', 'ctrgc_bwd', 'bn_finalize', 'bn_bwd_coef',
        'gcn_epilogue_fwd', 'gcn_epilogue_bwd', 'gcn_mid_bwd', 'tcn_epilogue_fwd', 'tcn_epilogue_bwd', 'maxpool_fwd',
        'maxpool_bwd', 'graph_agg_fwd', 'graph_agg_bwd', 'data_bn_fwd', 'data_bn_bwd', 'pool_fc_fwd', 'pool_fc_bwd',
-       'softmax_ce_fwd', 'softmax_ce_bwd', 'sgd_step', 'transpose_act']
+       'softmax_ce_fwd', 'softmax_ce_bwd', 'sgd_step', 'transpose_act', 'feeder_nucla']
 
 
 def install(monkeypatch=None):
