@@ -421,13 +421,16 @@ def step_roofline(replay, acct, n_steps, peak_gbs, peak_tf, ms_per_step):
         for _ in range(n_steps):
             replay()
         torch.cuda.synchronize()
-    fam_us, fam_n, other = {}, {}, {}
+    fam_us, fam_n, other, kern = {}, {}, {}, []
     total = 0.0
     for ev in prof.key_averages():
-        us = float(getattr(ev, 'device_time_total', 0.0) or getattr(ev, 'cuda_time_total', 0.0))
+        us = float(getattr(ev, 'device_time_total', 0.0) or 0.0)
+        if us <= 0:
+            us = float(getattr(ev, 'cuda_time_total', 0.0) or 0.0)
         if us <= 0:
             continue
         total += us
+        kern.append((us, ev.count, ev.key))
         for fam, pat in FAMILIES:
             if re.search(pat, ev.key):
                 fam_us[fam] = fam_us.get(fam, 0.0) + us
@@ -450,7 +453,9 @@ def step_roofline(replay, acct, n_steps, peak_gbs, peak_tf, ms_per_step):
         rows.append(row)
     if other:
         rows.append(dict(family='other', us_per_step=round(sum(other.values()) / n_steps, 1), kernels=sorted(other, key=other.get)[-5:]))
-    return dict(rows=rows, kernel_us_per_step=round(total / n_steps, 1), ms_per_step_timed=ms_per_step,
+    top = [dict(kernel=re.sub(r'^void |tamgcn::', '', k)[:90], us_per_step=round(u / n_steps, 1), launches_per_step=round(c / n_steps, 1),
+                us_per_launch=round(u / max(c, 1), 1)) for u, c, k in sorted(kern, reverse=True)[:16]]
+    return dict(rows=rows, top_kernels=top, kernel_us_per_step=round(total / n_steps, 1), ms_per_step_timed=ms_per_step,
                 note='device time summed over kernels from torch.profiler (CUPTI) over %d graph replays with warm L2; side-stream '
                      'kernels overlap, so the sum can exceed the step time. bytes/FLOPs: algorithmic, at the training shape' % n_steps)
 

@@ -720,6 +720,9 @@ static uint32_t al16(uint32_t x) { return (x + 15u) & ~15u; }
 int ctrgc_fwd_tc3(const void* x3, long long x3ns, int N, int Cout, int T, int V, int K, int R, const float* x1,
                   const float* x2, long long x12ns, const float* W4, const float* b4, const float* PA, const float* alpha,
                   void* y, long long yns, double* ssum, double* ssq, cudaStream_t st);
+int ctrgc_fwd_tc4(const void* x3, long long x3ns, int N, int Cout, int T, int V, int K, int R, const float* x1,
+                  const float* x2, long long x12ns, const float* W4, const float* b4, const float* PA, const float* alpha,
+                  void* y, long long yns, double* ssum, double* ssq, cudaStream_t st);
 
 // returns 1 if launched, 0 if the caller must use the SIMT kernel, <0 on error
 int ctrgc_fwd_tc(const void* x3, long long x3ns, int N, int Cout, int T, int V, int K, int R, const float* x1,
@@ -729,6 +732,9 @@ int ctrgc_fwd_tc(const void* x3, long long x3ns, int N, int Cout, int T, int V, 
     {   // the instruction-lean variant (ctrgc_tc3.cu) covers V = 20, R = 8, 32 < T <= 64
         const int rc3 = ctrgc_fwd_tc3(x3, x3ns, N, Cout, T, V, K, R, x1, x2, x12ns, W4, b4, PA, alpha, y, yns, ssum, ssq, st);
         if (rc3 != 0) return rc3;
+        // its V = 25 sibling (ctrgc_tc4.cu): V = 25, R = 8, 32 < T <= 64, T a multiple of 8
+        const int rc4 = ctrgc_fwd_tc4(x3, x3ns, N, Cout, T, V, K, R, x1, x2, x12ns, W4, b4, PA, alpha, y, yns, ssum, ssq, st);
+        if (rc4 != 0) return rc4;
     }
     if (V != 20 && V != 25) return 0;
     const int VS = V == 20 ? 20 : 32, VN = V == 20 ? 24 : 32, VP = V == 20 ? 20 : 28;

@@ -38,6 +38,10 @@ class GpuSkeletonFeeder:
             s = np.asarray(s, dtype=np.float32)
             raw[i, :s.shape[0]] = s
             length[i] = s.shape[0]
+        # evaluation frame grid of every sequence, computed once with numpy itself (feeder_nucla_gcn.py:116) — float64
+        # rounding of i * (L - 1) / (T - 1) decides the truncation, and device arithmetic is free to round differently
+        val_idx = np.stack([np.linspace(0, int(L) - 1, self.T).astype(int) for L in length]).astype(np.int32)
+        self.val_idx = torch.from_numpy(val_idx).to(self.device)
         self.raw = torch.from_numpy(raw).to(self.device)
         self.length = torch.from_numpy(length).to(self.device)
         self.labels = torch.as_tensor(np.asarray(labels), dtype=torch.int64).to(self.device)
@@ -56,10 +60,7 @@ class GpuSkeletonFeeder:
         L = self.length[sample].to(torch.int64)                                        # (B,)
         if not train:
             view = torch.tensor([0.0, 0.0, 1.0], device=dev).repeat(B, 1)
-            # np.linspace(0, L - 1, T).astype(int): numpy evaluates i * ((L - 1) / (T - 1)) in float64, end point exact
-            step = (L - 1).to(torch.float64) / (self.T - 1)
-            idx = (torch.arange(self.T, device=dev, dtype=torch.float64)[None, :] * step[:, None]).floor().to(torch.int32)
-            idx[:, -1] = (L - 1).to(torch.int32)                                       # linspace hits the end point exactly
+            idx = self.val_idx[sample]
             return view, idx.contiguous()
         ang = torch.randint(-60, 61, (B, 2), device=dev, generator=generator).to(torch.float32)
         sc = torch.rand((B, 1), device=dev, generator=generator) + 0.5
