@@ -1,4 +1,4 @@
-"""One eager (un-graphed) CTR-GCN training step between cudaProfilerStart/Stop, for
+"""One eager (un-graphed) training step (workload argv[3], default ucla_train) between cudaProfilerStart/Stop, for
    ncu --profile-from-start off --metrics gpu__time_duration.sum ...   (launch list of a step)."""
 import os
 import sys
@@ -14,11 +14,11 @@ dtype = torch.bfloat16 if (len(sys.argv) < 2 or sys.argv[1] == 'bf16') else torc
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 tam_gcn_b200.set_act_dtype(dtype)
 torch.manual_seed(0)
-model = ctrgcn.Model(**bench.UCLA)
-bench.perturb_(model.named_parameters())
-model = model.cuda().train()
-tr = engine.Trainer(model, use_graph=False)
-x, y = bench.synthetic_batch(batch, 1, 'cuda')
+wname = sys.argv[3] if len(sys.argv) > 3 else 'ucla_train'
+w = bench.WORKLOADS[wname]
+model = bench.build_model(w, 'cuda').train()
+tr = engine.Trainer(model, use_graph=False, side_stream=False)
+x, y = bench.synthetic_batch(w, batch, 1, 'cuda')
 for _ in range(3):
     tr.step(x, y)
 torch.cuda.synchronize()

@@ -49,6 +49,7 @@ struct C3P {
     int N, Cout, T, K;
     long long x3ns, x12ns, yns;
     int nCG, n_tiles, S;
+    int pf;                      // L2 prefetch distance in tiles (0 = off)
     uint32_t off_D, off_PA, off_W4, off_b4, off_out, off_stat, off_hdr, off_x12;
 };
 
@@ -285,12 +286,23 @@ ctrgc_fwd_tc3_kernel(C3P p, const bf16* __restrict__ x3, const float* __restrict
                 doff[k] = row * 128u + (((byte >> 4) ^ (row & 7u)) << 4) + (byte & 15u);
             }
         }
+        // L2 prefetch `pf` tiles ahead (one lane): the 4 channels of a subset are contiguous (4 * T * 40 bytes)
+        const uint32_t pbytes = (uint32_t)(4 * T * C3_V * 2);
+        auto prefetch_tile = [&](int tile) {
+            const int pn = tile / p.nCG, pcg = tile - pn * p.nCG;
+            const bf16* b = x3 + (long long)pn * p.x3ns + (long long)(pcg * 4) * T * C3_V;
+            for (int i = 0; i < K; ++i) bulk_prefetch_l2(b + (long long)i * p.Cout * T * C3_V, pbytes);
+        };
+        const bool pf_lane = p.pf > 0 && lt == 32 && (pbytes & 15u) == 0;   // second loader warp: the first one polls the barrier
+        if (pf_lane)
+            for (int k = 1; k < p.pf && k < nt; ++k) prefetch_tile(tile_begin + k);
         int n = tile_begin / p.nCG, cg = tile_begin - n * p.nCG;
         for (int it = 0; it < nt; ++it) {
             const int c0 = cg * 4;
             const int s = it % S, ph = (it / S) & 1;
             const uint32_t sA = s0 + (uint32_t)s * C3_STAGE_BYTES;
             const bf16* xn = x3 + (long long)n * p.x3ns;
+            if (pf_lane && it + p.pf < nt) prefetch_tile(tile_begin + it + p.pf);
             if (lt < 32) c3_wait(hdr, &hdr->empty[s], (uint32_t)(ph ^ 1));
             c3_bar_sync(4, C3_LD_T);
             // units k < kfull exist for every thread of the role: issued without a predicate (a predicated cp.async costs
@@ -493,6 +505,9 @@ int ctrgc_fwd_tc3(const void* x3, long long x3ns, int N, int Cout, int T, int V,
     p.off_hdr = off; off += szH;
     p.off_x12 = off; off += szX;
     const size_t sm = (size_t)off + 1024;
+    // x3 rows must be 16-byte aligned blocks for the bulk prefetch (the 8-byte gathers only need 8)
+    { static const int pf = [] { const char* e = getenv("TAMGCN_C3_PF"); return e ? atoi(e) : 0; }();
+      p.pf = (((uintptr_t)x3 & 15) == 0 && (x3ns & 7) == 0) ? pf : 0; }
     int grid = c3_num_sms();
     if (grid > p.n_tiles) grid = p.n_tiles;
     static SmemLimit lim;

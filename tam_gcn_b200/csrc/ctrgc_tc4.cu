@@ -51,6 +51,7 @@ struct C4P {
     int N, Cout, T, K;
     long long x3ns, x12ns, yns;
     int nCG, n_tiles, S;
+    int pf;                      // L2 prefetch distance in tiles (0 = off)
     int dbg;                     // TAMGCN_C4_DBG (profiling aid): 1 skip x3 loads, 2 skip Q math, 4 skip output, 8 skip realign
     uint32_t off_D, off_PA, off_W4, off_b4, off_out, off_stat, off_hdr, off_x12;
 };
@@ -333,11 +334,21 @@ ctrgc_fwd_tc4_kernel(C4P p, const bf16* __restrict__ x3, const float* __restrict
                     if (ok && i < K) st_shared_v4(sa + (uint32_t)i * C4_A_BLK + (uint32_t)g * 4096u + dst_r, v.x, v.y, v.z, v.w);
                 }
         };
+        // L2 prefetch `pf` tiles ahead (loader warp 0, one lane): the 4 channels of a subset are contiguous (4 * ps bytes)
+        auto prefetch_tile = [&](int tile) {
+            const int pn = tile / p.nCG, pcg = tile - pn * p.nCG;
+            const uint8_t* b = reinterpret_cast<const uint8_t*>(x3 + (long long)pn * p.x3ns) + (uint32_t)(pcg * 4) * ps;
+            for (int i = 0; i < K; ++i) bulk_prefetch_l2(b + (uint32_t)i * sub, 4u * ps);
+        };
+        const bool pf_lane = p.pf > 0 && lw == 0 && lane == 0;
+        if (pf_lane)
+            for (int k = 1; k < p.pf && k < nt; ++k) prefetch_tile(tile_begin + k);
         uint4 wa[6], wb[6];
         if (nt > 0) load6(wa, tile_ptr(n, cg));
         for (int it = 0; it < nt; ++it) {
             const int s = it % S, ph = (it / S) & 1;
             const uint32_t sA = s0 + (uint32_t)s * C4_STAGE_BYTES;
+            if (pf_lane && it + p.pf < nt) prefetch_tile(tile_begin + it + p.pf);
             load6(wb, tile_ptr(n, cg) + 2u * ps);
             c4_wait(hdr, &hdr->empty[s], (uint32_t)(ph ^ 1));               // every lane polls: the warp stays converged
             store6(wa, sA);
@@ -499,6 +510,7 @@ int ctrgc_fwd_tc4(const void* x3, long long x3ns, int N, int Cout, int T, int V,
     if (fixed + 2u * C4_STAGE_BYTES > budget) return 0;
     p.S = C4_SMAX;
     { const char* e = getenv("TAMGCN_C4_DBG"); p.dbg = e ? atoi(e) : 0; }
+    { static const int pf = [] { const char* e = getenv("TAMGCN_C4_PF"); return e ? atoi(e) : 2; }(); p.pf = pf; }
     uint32_t off = (uint32_t)p.S * C4_STAGE_BYTES;
     p.off_D = off; off += szD;                                  // D and PA must directly follow the stages (zero fill)
     p.off_PA = off; off += szPA;

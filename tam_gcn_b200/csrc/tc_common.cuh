@@ -29,6 +29,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a contiguous global range (16-byte aligned address, size a multiple of 16): one instruction, no
+// destination, no completion to wait for.  Persistent CTAs use it a few tiles ahead of their loaders so that the loads
+// proper see L2 latency instead of HBM latency.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // Bounded wait (a wedged pipeline must not hang the GPU): returns false after ~2 s.  The suspend-time hint lets the
 // hardware park the warp for a while instead of re-polling at once, but the parking time is bounded by the
 // implementation and failed probes are common, so the retry path is kept to three instructions (probe, two
