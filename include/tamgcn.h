@@ -33,6 +33,10 @@ enum { TAMGCN_RES_NONE = 0, TAMGCN_RES_IDENTITY = 1, TAMGCN_RES_AFFINE = 2 };
 
 int tamgcn_version(void);
 const char* tamgcn_last_error(void);
+/* Share (percent, 1..100; default 100) of the SMs the persistent weight-gradient kernels launched by the CALLING
+ * THREAD may occupy; returns the previous value.  A step engine that launches weight gradients on a side stream sets
+ * ~50 so that they run next to — not in turns with — the data-gradient chain of the main stream. */
+int tamgcn_set_wgrad_sm_share(int percent);
 /* number of kernel launches issued by this library in the calling process (bench.py gpu_launches) */
 int64_t tamgcn_launch_count(void);
 

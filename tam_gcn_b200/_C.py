@@ -90,6 +90,8 @@ def lib():
         l.tamgcn_version.restype = i32
         l.tamgcn_last_error.restype = C.c_char_p
         l.tamgcn_launch_count.restype = i64
+        l.tamgcn_set_wgrad_sm_share.restype = i32
+        l.tamgcn_set_wgrad_sm_share.argtypes = [i32]
         l.tamgcn_conv_pack_bytes.restype = i64
         l.tamgcn_conv_pack_bytes.argtypes = [i32, i32, i32, i32]
         for name, args in SIGNATURES.items():

@@ -43,6 +43,15 @@ static inline void ensure_smem(K kernel, SmemLimit& lim, size_t bytes) {
     if ((int)bytes > lim.cur[dev].load(std::memory_order_acquire)) raise_smem_limit((const void*)kernel, lim, dev, bytes);
 }
 
+// Share (percent, 1..100) of the SMs that the persistent weight-gradient kernels of the calling thread may occupy.
+// The engine launches them on a side stream next to the data-gradient chain: at 100 % they grab every SM and the
+// two streams merely alternate, at ~50 % both run at once (tamgcn_set_wgrad_sm_share; thread-local, default 100).
+int wgrad_sm_share();
+static inline int wgrad_sms() {
+    const int n = num_sms() * wgrad_sm_share() / 100;
+    return n < 1 ? 1 : n;
+}
+
 #define TG_REQUIRE(cond, ...)                       \
     do {                                            \
         if (!(cond)) return tamgcn::set_error(__VA_ARGS__); \

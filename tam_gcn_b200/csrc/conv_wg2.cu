@@ -363,12 +363,36 @@ conv_wg2_kernel(W2P p, Opnd dyo, Opnd xo, float* __restrict__ dW, float* __restr
         if (j < k && ci < nci) atomicAdd(dW + (long long)(co0 + row) * CK + (ci0 + ci) * k + j, acc[c]);          \
         else if (do_bias && j == 0 && ci == NT) atomicAdd(dbias + co0 + row, acc[c]);                             \
     }
+        // k = 1: the 16 columns a thread holds are 64 contiguous bytes of its dW row -> 16-byte vector reductions
+        // (red.global.add.v4.f32): a quarter of the atomic instructions and L2 atomic transactions
+        const bool vec4 = k == 1 && (CK & 3) == 0 && (ci0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0);
         for (int bb = grp; bb < nblk; bb += 3) {
             int b = bb + rot_b;
             if (b >= nblk) b -= nblk;
             float acc[16];
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 16), acc);
-            if (row < nco && !hdr->error) {
+            if (vec4 && row < nco && !hdr->error) {
+                float* rowp = dW + (long long)(co0 + row) * CK + ci0;
+#define W2_DRAIN_V4(R)                                                                                            \
+    _Pragma("unroll") for (int g4 = 0; g4 < 4; ++g4) {                                                            \
+        const int c4 = ((g4 + (R)) & 3) * 4;                                                                       \
+        const int ci = b * 16 + c4;                                                                                \
+        if (ci + 3 < nci) {                                                                                        \
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(rowp + ci), "f"(acc[c4]),           \
+                         "f"(acc[c4 + 1]), "f"(acc[c4 + 2]), "f"(acc[c4 + 3]) : "memory");                         \
+        } else {                                                                                                   \
+            _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
+                if (ci + e < nci) atomicAdd(rowp + ci + e, acc[c4 + e]);                                            \
+                else if (do_bias && ci + e == NT) atomicAdd(dbias + co0 + row, acc[c4 + e]);                       \
+            }                                                                                                      \
+        }                                                                                                          \
+    }
+                if (rot_c == 0) { W2_DRAIN_V4(0) }
+                else if (rot_c == 1) { W2_DRAIN_V4(1) }
+                else if (rot_c == 2) { W2_DRAIN_V4(2) }
+                else { W2_DRAIN_V4(3) }
+#undef W2_DRAIN_V4
+            } else if (row < nco && !hdr->error) {
                 if (rot_c == 0) { W2_DRAIN_COLS(0) }
                 else if (rot_c == 1) { W2_DRAIN_COLS(4) }
                 else if (rot_c == 2) { W2_DRAIN_COLS(8) }
@@ -452,7 +476,7 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     p.off_coef = p.off_hdr + szH;
     const size_t sm = (size_t)p.off_coef + szC + 1024;
     const int gx = (g.Cout + 127) / 128, gy = (g.Cin + NT - 1) / NT;
-    long long Z = (long long)occ * w2_num_sms() / (gx * gy);
+    long long Z = (long long)occ * wgrad_sms() / (gx * gy);
     if (Z < 1) Z = 1;
     if (Z > units) Z = units;
     if (Z > 65535) Z = 65535;

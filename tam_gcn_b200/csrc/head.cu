@@ -144,17 +144,27 @@ data_bn_bwd_kernel(DataBnP p, const T* __restrict__ g, const float* __restrict__
 }
 
 // ---- global average pool + linear ----------------------------------------------------------------------------------
-// one CTA per sample n: pooled[n,c] = mean over (m, t, v) of x[n*M+m, c, :, :];  logits[n,k] = b[k] + sum_c W[k,c]*pooled[n,c]
+// pooled[n,c] = mean over (m, t, v) of x[n*M+m, c, :, :];  logits[n,k] = b[k] + sum_c W[k,c]*gate[n,c]*pooled[n,c]
 // (x.view(N,M,C,-1).mean(3).mean(1) == mean over all M*TV elements since every person has the same TV)
+// phase 0: one CTA per sample does both (small planes: one launch).  Large planes with few samples (ST-GCN: 16 samples
+// x 2 persons x 75 x 25 positions) would leave most SMs idle, so the work is split: phase 1 pools a slice of CS channels
+// per CTA (grid N x C/CS), phase 2 (grid N) reads the pooled vector back and applies the classifier.
 template <typename T>
 __global__ void __launch_bounds__(256)
-pool_fc_fwd_kernel(int N, int M, int C, int TV, int K, const T* __restrict__ x, const float* __restrict__ gate,
-                   const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ pooled,
-                   float* __restrict__ logits) {
+pool_fc_fwd_kernel(int N, int M, int C, int TV, int K, int phase, int CS, const T* __restrict__ x,
+                   const float* __restrict__ gate, const float* __restrict__ W, const float* __restrict__ b,
+                   float* __restrict__ pooled, float* __restrict__ logits) {
     extern __shared__ float sp[];                       // C floats
     const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float inv = 1.f / (float)(M * TV);
-    for (int c = w; c < C; c += nw) {
+    const int c_lo = phase == 1 ? blockIdx.y * CS : 0, c_hi = phase == 1 ? min(C, c_lo + CS) : C;
+    if (phase == 2) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float s = pooled[(long long)n * C + c];
+            sp[c] = gate ? s * __ldg(gate + (long long)n * C + c) : s;
+        }
+    } else
+    for (int c = c_lo + w; c < c_hi; c += nw) {
         float s = 0.f;
         for (int m = 0; m < M; ++m) {
             const T* px = x + ((long long)(n * M + m) * C + c) * TV;
@@ -167,7 +177,7 @@ pool_fc_fwd_kernel(int N, int M, int C, int TV, int K, const T* __restrict__ x, 
         }
     }
     __syncthreads();
-    if (!W) return;
+    if (!W || phase == 1) return;
     for (int k = w; k < K; k += nw) {
         float s = 0.f;
         for (int c = lane; c < C; c += 32) s = fmaf(__ldg(W + (long long)k * C + c), sp[c], s);
@@ -182,19 +192,20 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pool_fc_bwd_kernel(int N, int M, int C, int TV, int K, const float* __restrict__ dl, const float* __restrict__ pooled,
                    const float* __restrict__ gate, const float* __restrict__ W, T* __restrict__ g, float* dW, float* db,
-                   float* __restrict__ dgate) {
+                   float* __restrict__ dgate, int CS) {
     extern __shared__ float sm[];                       // K floats dl, C floats dpooled
     float* sdl = sm;
     float* sdp = sm + K;
     const int n = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int c_lo = blockIdx.y * CS, c_hi = min(C, c_lo + CS);      // this CTA's channel slice (grid N x C/CS)
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const float v = __ldg(dl + (long long)n * K + k);
         sdl[k] = v;
-        if (db) atomicAdd(db + k, v);
+        if (db && blockIdx.y == 0) atomicAdd(db + k, v);
     }
     __syncthreads();
     const float inv = 1.f / (float)(M * TV);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
         float s = 0.f;
         const float gt = gate ? __ldg(gate + (long long)n * C + c) : 1.f;
         if (W) {
@@ -212,8 +223,9 @@ pool_fc_bwd_kernel(int N, int M, int C, int TV, int K, const float* __restrict__
     }
     __syncthreads();
     if (!g) return;
-    for (int mc = w; mc < M * C; mc += nw) {
-        const int m = mc / C, c = mc - m * C;
+    const int cs = c_hi - c_lo;
+    for (int mc = w; mc < M * cs; mc += nw) {
+        const int m = mc / cs, c = c_lo + (mc - m * cs);
         const float v = sdp[c];
         T* pg = g + ((long long)(n * M + m) * C + c) * TV;
         for (int e = lane; e < TV; e += 32) stf<T>(pg + e, v);
@@ -390,11 +402,23 @@ extern "C" int tamgcn_pool_fc_fwd(int dtype, const void* x, int N, int M, int C,
     TG_REQUIRE(C * sizeof(float) <= 48 * 1024, "pool_fc_fwd: C=%d too large", C);
     TG_REQUIRE(dtype == TAMGCN_F32 || dtype == TAMGCN_BF16, "pool_fc_fwd: bad dtype %d", dtype);
     const size_t sm = C * sizeof(float);
-    if (dtype == TAMGCN_F32)
-        pool_fc_fwd_kernel<float><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, (const float*)x, gate, W, b, pooled, logits);
-    else
-        pool_fc_fwd_kernel<bf16><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, (const bf16*)x, gate, W, b, pooled, logits);
-    count_launch();
+    cudaStream_t st = (cudaStream_t)stream;
+    // few samples with large planes: split into a channel-sliced pooling launch and a classifier launch
+    const bool split = (long long)N * 2 < num_sms() && (long long)M * TV >= 1024 && C >= 32;
+    const int CS = 16;
+    auto launch = [&](dim3 grid, int phase) {
+        if (dtype == TAMGCN_F32)
+            pool_fc_fwd_kernel<float><<<grid, 256, sm, st>>>(N, M, C, TV, K, phase, CS, (const float*)x, gate, W, b, pooled, logits);
+        else
+            pool_fc_fwd_kernel<bf16><<<grid, 256, sm, st>>>(N, M, C, TV, K, phase, CS, (const bf16*)x, gate, W, b, pooled, logits);
+        count_launch();
+    };
+    if (!split) {
+        launch(dim3(N), 0);
+    } else {
+        launch(dim3(N, (C + CS - 1) / CS), 1);
+        if (W) launch(dim3(N), 2);
+    }
     return check_launch("pool_fc_fwd");
 }
 
@@ -406,10 +430,14 @@ extern "C" int tamgcn_pool_fc_bwd(int dtype, const float* dlogits, const float* 
     TG_REQUIRE((size_t)(C + K) * sizeof(float) <= 48 * 1024, "pool_fc_bwd: C+K too large");
     TG_REQUIRE(dtype == TAMGCN_F32 || dtype == TAMGCN_BF16, "pool_fc_bwd: bad dtype %d", dtype);
     const size_t sm = (size_t)(C + K) * sizeof(float);
+    // channel slices per CTA: enough CTAs to fill the chip when there are few samples
+    int CS = C;
+    while (CS > 16 && (long long)N * ((C + CS - 1) / CS) < 2LL * num_sms()) CS = (CS + 1) / 2;
+    dim3 grid(N, (C + CS - 1) / CS);
     if (dtype == TAMGCN_F32)
-        pool_fc_bwd_kernel<float><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, gate, W, (float*)g, dW, db, dgate);
+        pool_fc_bwd_kernel<float><<<grid, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, gate, W, (float*)g, dW, db, dgate, CS);
     else
-        pool_fc_bwd_kernel<bf16><<<N, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, gate, W, (bf16*)g, dW, db, dgate);
+        pool_fc_bwd_kernel<bf16><<<grid, 256, sm, (cudaStream_t)stream>>>(N, M, C, TV, K, dlogits, pooled, gate, W, (bf16*)g, dW, db, dgate, CS);
     count_launch();
     return check_launch("pool_fc_bwd");
 }

@@ -27,6 +27,9 @@ int check_launch(const char* what) {
     return 0;
 }
 
+static thread_local int g_wgrad_share = 100;
+int wgrad_sm_share() { return g_wgrad_share; }
+
 int current_device() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -56,6 +59,11 @@ void raise_smem_limit(const void* kernel, SmemLimit& lim, int dev, size_t bytes)
 
 }  // namespace tamgcn
 
+extern "C" int tamgcn_set_wgrad_sm_share(int percent) {
+    const int old = tamgcn::g_wgrad_share;
+    if (percent >= 1 && percent <= 100) tamgcn::g_wgrad_share = percent;
+    return old;
+}
 extern "C" int tamgcn_version(void) { return 100; }
 extern "C" const char* tamgcn_last_error(void) { return tamgcn::g_err; }
 extern "C" int64_t tamgcn_launch_count(void) { return (int64_t)tamgcn::g_launches.load(); }

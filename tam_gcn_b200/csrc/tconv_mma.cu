@@ -431,7 +431,7 @@ static bool tm_setup(TmP& p, const tamgcn_conv_geom* g, int kind, size_t& smem) 
                 const size_t sm_c = (size_t)CB * tm_oddpitch(((TB * NTW + 1) / 2) * 16) * 2 + (size_t)CB * tm_oddpitch(RIN * p.VP) * 2 + 6 * CB * 4;
                 if (sm_c > 100 * 1024) continue;
                 const long long units = (long long)p.N * ((p.Tout + TB - 1) / TB);
-                const long long rounds = (units + tm_num_sms() - 1) / tm_num_sms();
+                const long long rounds = (units + wgrad_sms() - 1) / wgrad_sms();
                 const long long cost = rounds * (RIN + 4);
                 if (best < 0 || cost < best) { best = cost; best_tps = cand; }
             }
@@ -510,7 +510,7 @@ int tconv_mma_wgrad(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, fl
     p.vec_in2 = tm_vec(x, p.V);
     const int CB = g->Cin, NTW = p.VP / 8;
     long long grid = (long long)p.N * p.tps;
-    if (grid > tm_num_sms()) grid = tm_num_sms();
+    if (grid > wgrad_sms()) grid = wgrad_sms();
     tm_dispatch(CB, NTW, [&](auto cb, auto ntw) {
         constexpr int CB_ = decltype(cb)::value, NTW_ = decltype(ntw)::value;
         if (g->k == 5) {

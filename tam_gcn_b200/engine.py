@@ -31,7 +31,7 @@ from .params import ParamStore
 
 class Trainer:
     def __init__(self, model, lr=0.1, momentum=0.9, nesterov=True, weight_decay=1e-4, use_graph=True,
-                 process_group=None, side_stream=True, overlap_allreduce=True, loss_fn=None):
+                 process_group=None, side_stream=True, overlap_allreduce=True, loss_fn=None, wgrad_sm_share=None):
         self.model = model
         self.store = ParamStore(model)
         self.device = self.store.device
@@ -46,6 +46,8 @@ class Trainer:
         self.arena = _arena.ZeroArena(self.device)
         self._arena_keep = []                       # buffers baked into captured graphs: never freed
         self.side = torch.cuda.Stream(device=self.device) if (self.cuda and side_stream) else None
+        import os
+        self.wgrad_sm_share = int(wgrad_sm_share or os.environ.get('TAMGCN_WGRAD_SM_SHARE', 50))
         self.overlap = bool(overlap_allreduce) and self.world > 1 and self.cuda
         self.graph = None
         self.static_x = self.static_y = self.static_loss = None
@@ -133,7 +135,7 @@ class Trainer:
         self._pending = None
         self._armed = self.overlap and self._split is not None
         try:
-            with _arena.use(self.arena), st.direct_grads(), ops.side_stream(self.side):
+            with _arena.use(self.arena), st.direct_grads(), ops.side_stream(self.side, self.wgrad_sm_share):
                 out = self.model(x)
                 loss = self.loss_fn(out, y)
                 loss.backward()

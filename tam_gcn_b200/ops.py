@@ -35,20 +35,23 @@ def _stream():
 # Every tensor such a launch touches is kept referenced until `join_side_stream`, so the caching allocator cannot hand
 # its memory to a later kernel of the main stream while the side stream still reads it.
 class _Side:
-    __slots__ = ('stream', 'keep')
+    __slots__ = ('stream', 'keep', 'share')
 
-    def __init__(self, stream):
-        self.stream, self.keep = stream, []
+    def __init__(self, stream, share=100):
+        self.stream, self.keep, self.share = stream, [], int(share)
 
 
 _side = None
 
 
 @contextlib.contextmanager
-def side_stream(stream):
+def side_stream(stream, sm_share=50):
+    """Weight-gradient kernels of the calling thread go to `stream` and may occupy `sm_share` percent of the SMs
+    (measured on the NW-UCLA step: 100 % -> the two streams alternate, 50 % -> they overlap, 25 % -> the side stream
+    becomes the critical path)."""
     global _side
     old = _side
-    _side = _Side(stream) if stream is not None else None
+    _side = _Side(stream, sm_share) if stream is not None else None
     try:
         yield
     finally:
@@ -258,7 +261,12 @@ def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
         return
     sd.stream.wait_stream(torch.cuda.current_stream())
     sd.keep.append(_opnd_tensors(dy) + _opnd_tensors(x) + (dW, dbias))
-    _C.check(_C.lib().tamgcn_conv_wgrad(*args, sd.stream.cuda_stream), 'tamgcn_conv_wgrad')
+    # the SM share is thread-local in the library and backward runs on autograd's device thread: set it around the call
+    prev = _C.lib().tamgcn_set_wgrad_sm_share(sd.share)
+    try:
+        _C.check(_C.lib().tamgcn_conv_wgrad(*args, sd.stream.cuda_stream), 'tamgcn_conv_wgrad')
+    finally:
+        _C.lib().tamgcn_set_wgrad_sm_share(prev)
 
 
 def mean_t(x, m):

@@ -94,7 +94,7 @@ def test_data_bn_three_dim_input_and_aten():
 
 
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize('cfg', [(64, 1, 256, 13, 20, 10), (6, 2, 256, 16, 25, 60), (3, 3, 40, 5, 20, 7)])
+@pytest.mark.parametrize('cfg', [(64, 1, 256, 13, 20, 10), (6, 2, 256, 16, 25, 60), (3, 3, 40, 5, 20, 7), (4, 2, 256, 75, 25, 60)])
 def test_pool_fc_and_cross_entropy(dt, cfg):
     dev = _dev()
     from tam_gcn_b200 import ops
