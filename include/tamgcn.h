@@ -33,10 +33,13 @@ enum { TAMGCN_RES_NONE = 0, TAMGCN_RES_IDENTITY = 1, TAMGCN_RES_AFFINE = 2 };
 
 int tamgcn_version(void);
 const char* tamgcn_last_error(void);
-/* Share (percent, 1..100; default 100) of the SMs the persistent weight-gradient kernels launched by the CALLING
- * THREAD may occupy; returns the previous value.  A step engine that launches weight gradients on a side stream sets
- * ~50 so that they run next to — not in turns with — the data-gradient chain of the main stream. */
+/* Share (percent, 1..100; default 100; process-wide) of the SMs the persistent weight-gradient kernels may occupy;
+ * returns the previous value.  A step engine that launches weight gradients on a side stream sets ~50 so that they run
+ * next to — not in turns with — the data-gradient chain of the main stream.  tamgcn_set_main_sm_share does the same for
+ * the persistent convolution forward / data-gradient kernels (so that, while the side stream holds part of the chip, a
+ * main-stream kernel is not split into a running and a waiting wave of CTAs). */
 int tamgcn_set_wgrad_sm_share(int percent);
+int tamgcn_set_main_sm_share(int percent);
 /* number of kernel launches issued by this library in the calling process (bench.py gpu_launches) */
 int64_t tamgcn_launch_count(void);
 
@@ -149,6 +152,9 @@ typedef struct tamgcn_bn_bwd {
     int32_t reserved;
 } tamgcn_bn_bwd;
 int tamgcn_bn_bwd_coef(int n_bn, const tamgcn_bn_bwd* bns, double count, int train, tamgcn_stream stream);
+/* coefficients of the lazily formed difference res - y of unit_gcn (models/ctrgcn.py:256-259), per channel:
+ * nb = -sb, c = (ha ? ha : 0) - hb */
+int tamgcn_coef_diff(int C, const float* sb, const float* ha, const float* hb, float* nb, float* c, tamgcn_stream stream);
 
 /* ---- fused epilogues (BN + tanh/ReLU + residual): models/ctrgcn.py:255-261,145-146,283; stgcn.py:98-99 */
 /* out = relu( sg*y0+hg + tanh(so*z+ho) + res );  res = 0 | r | sr*r+hr */
@@ -159,11 +165,13 @@ int tamgcn_gcn_epilogue_fwd(int dtype, int N, int C, int TV, const void* y0, con
 int tamgcn_gcn_epilogue_bwd(int dtype, int N, int C, int TV, const void* g, const void* out, const void* z,
                             const float* so, const float* ho, void* G, void* DZ, double* s1o, double* s2o,
                             tamgcn_stream stream);
-/* DY = G - DD (in place over G);  DR = G + DD (to dr, may be NULL);  s1g += sum DY; s2g += sum DY*y0;
- * s1d += sum DR; s2d += sum DR*r (r, s1d, s2d may be NULL) */
+/* DY = G - DD (in place over G);  DR = G + DD (+ extra) (to dr, may be NULL);  s1g += sum DY; s2g += sum DY*y0;
+ * s1d += sum DR; s2d += sum DR*r (r, s1d, s2d may be NULL).  `extra` (may be NULL; only without r): a further cotangent
+ * of the identity residual — the gradient TCN_GCN_unit's own residual sends to the same input (models/ctrgcn.py:283) —
+ * so that no separate add pass is needed. */
 int tamgcn_gcn_mid_bwd(int dtype, int N, int C, int TV, void* G, const void* DD, void* dr, int64_t dr_nstride,
                        const void* y0, const void* r, int64_t r_nstride, double* s1g, double* s2g, double* s1d,
-                       double* s2d, tamgcn_stream stream);
+                       double* s2d, const void* extra, int64_t extra_nstride, tamgcn_stream stream);
 /* out = f( su*u+hu + res ), f = relu if relu else identity */
 int tamgcn_tcn_epilogue_fwd(int dtype, int N, int C, int TV, const void* u, int64_t u_nstride, const float* su,
                             const float* hu, int res_mode, const void* r, int64_t r_nstride, const float* sr,

@@ -57,7 +57,8 @@ SIGNATURES = {
     'tamgcn_bn_bwd_coef': [i32, C.POINTER(BnBwdDesc), f64, i32, vp],
     'tamgcn_gcn_epilogue_fwd': [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp, vp],
     'tamgcn_gcn_epilogue_bwd': [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
-    'tamgcn_gcn_mid_bwd': [i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp],
+    'tamgcn_gcn_mid_bwd': [i32, i32, i32, i32, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp],
+    'tamgcn_coef_diff': [i32, vp, vp, vp, vp, vp, vp],
     'tamgcn_tcn_epilogue_fwd': [i32, i32, i32, i32, vp, i64, vp, vp, i32, vp, i64, vp, vp, i32, vp, vp],
     'tamgcn_tcn_epilogue_bwd': [i32, i32, i32, i32, vp, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp],
     'tamgcn_maxpool_fwd': [i32, i32, i32, i32, i32, i32, i32, OP, vp, i64, vp, vp, vp],
@@ -92,6 +93,8 @@ def lib():
         l.tamgcn_launch_count.restype = i64
         l.tamgcn_set_wgrad_sm_share.restype = i32
         l.tamgcn_set_wgrad_sm_share.argtypes = [i32]
+        l.tamgcn_set_main_sm_share.restype = i32
+        l.tamgcn_set_main_sm_share.argtypes = [i32]
         l.tamgcn_conv_pack_bytes.restype = i64
         l.tamgcn_conv_pack_bytes.argtypes = [i32, i32, i32, i32]
         for name, args in SIGNATURES.items():

@@ -73,9 +73,28 @@ bn_bwd_coef_kernel(BnBwdPack pk, double count, int train) {
     }
 }
 
+// coefficients of the lazily formed difference  res - y  of unit_gcn (models/ctrgcn.py:256-259):
+//   nb = -sb,  c = (ha ? ha : 0) - hb
+__global__ void __launch_bounds__(256)
+coef_diff_kernel(int C, const float* __restrict__ sb, const float* __restrict__ ha, const float* __restrict__ hb,
+                 float* __restrict__ nb, float* __restrict__ c) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x) {
+        nb[i] = -sb[i];
+        c[i] = (ha ? ha[i] : 0.f) - hb[i];
+    }
+}
+
 }  // namespace tamgcn
 
 using namespace tamgcn;
+
+extern "C" int tamgcn_coef_diff(int C, const float* sb, const float* ha, const float* hb, float* nb, float* c,
+                                tamgcn_stream stream) {
+    TG_REQUIRE(C > 0 && sb && hb && nb && c, "coef_diff: bad arguments");
+    coef_diff_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(C, sb, ha, hb, nb, c);
+    count_launch();
+    return check_launch("coef_diff");
+}
 
 extern "C" int tamgcn_bn_finalize(int n_bn, const tamgcn_bn* bns, double count, float momentum, float eps, int train,
                                   tamgcn_stream stream) {

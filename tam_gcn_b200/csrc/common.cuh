@@ -45,8 +45,14 @@ static inline void ensure_smem(K kernel, SmemLimit& lim, size_t bytes) {
 
 // Share (percent, 1..100) of the SMs that the persistent weight-gradient kernels of the calling thread may occupy.
 // The engine launches them on a side stream next to the data-gradient chain: at 100 % they grab every SM and the
-// two streams merely alternate, at ~50 % both run at once (tamgcn_set_wgrad_sm_share; thread-local, default 100).
+// two streams merely alternate, at ~50 % both run at once (tamgcn_set_wgrad_sm_share / tamgcn_set_main_sm_share:
+// process-wide, default 100; the main share applies to the persistent convolution forward / data-gradient kernels).
 int wgrad_sm_share();
+int main_sm_share();
+static inline int main_sms() {
+    const int n = num_sms() * main_sm_share() / 100;
+    return n < 1 ? 1 : n;
+}
 static inline int wgrad_sms() {
     const int n = num_sms() * wgrad_sm_share() / 100;
     return n < 1 ? 1 : n;

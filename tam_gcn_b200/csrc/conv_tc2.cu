@@ -600,7 +600,7 @@ static bool c2_disabled() {
     }
     return v == 1;
 }
-static int c2_num_sms() { return num_sms(); }
+static int c2_num_sms() { return main_sms(); }
 static int oc_pad128(int OC) { return (OC + 127) & ~127; }
 
 size_t conv_pack_bytes(int Cout, int Cin, int k, int dgrad) {

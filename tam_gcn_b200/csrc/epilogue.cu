@@ -81,12 +81,12 @@ gcn_epilogue_bwd_kernel(int N, int C, int TV, const T* __restrict__ g, const T* 
     flush_stats<2>(acc, dst, c);
 }
 
-// DY = G - DD (in place over G);  DR = G + DD -> dr;  BN-backward sums for bn (y0) and down.bn (r)
+// DY = G - DD (in place over G);  DR = G + DD (+ extra) -> dr;  BN-backward sums for bn (y0) and down.bn (r)
 template <typename T>
 __global__ void __launch_bounds__(256)
 gcn_mid_bwd_kernel(int N, int C, int TV, T* __restrict__ G, const T* __restrict__ DD, T* __restrict__ dr,
                    long long drns, const T* __restrict__ y0, const T* __restrict__ r, long long rns, double* s1g,
-                   double* s2g, double* s1d, double* s2d) {
+                   double* s2g, double* s1d, double* s2d, const T* __restrict__ extra, long long exns) {
     const int c = blockIdx.x;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int n = blockIdx.y; n < N; n += gridDim.y) {
@@ -95,7 +95,8 @@ gcn_mid_bwd_kernel(int N, int C, int TV, T* __restrict__ G, const T* __restrict_
         const T* pr = r ? r + (long long)n * rns + (long long)c * TV : nullptr;
         for (int e = threadIdx.x; e < TV; e += blockDim.x) {
             const float gv = ldf<T>(G + base + e), dd = ldf<T>(DD + base + e);
-            const float dy = rnd<T>(gv - dd), drv = rnd<T>(gv + dd);
+            const float ex = extra ? ldf<T>(extra + (long long)n * exns + (long long)c * TV + e) : 0.f;
+            const float dy = rnd<T>(gv - dd), drv = rnd<T>(gv + dd + ex);
             stf<T>(G + base + e, dy);
             acc[0] += dy;
             acc[1] = fmaf(dy, ldf<T>(y0 + base + e), acc[1]);
@@ -260,19 +261,21 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 gcn_mid_bwd_vec_kernel(int N, int C, int TV, bf16* __restrict__ G, const bf16* __restrict__ DD, bf16* __restrict__ dr,
                        long long drns, const bf16* __restrict__ y0, const bf16* __restrict__ r, long long rns, double* s1g,
-                       double* s2g, double* s1d, double* s2d) {
+                       double* s2g, double* s1d, double* s2d, const bf16* __restrict__ extra, long long exns) {
     const int c = blockIdx.x, TVv = TV / VEC;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     BV_WALK_BEGIN(N, TVv)
         const long long off = ((long long)n * C + c) * TV + (long long)e * VEC;
         const BVec<VEC> vg = bv_ld<VEC>(G + off), vd = bv_ld<VEC>(DD + off), vy = bv_ld<VEC>(y0 + off);
-        BVec<VEC> vr, oY, oR;
+        BVec<VEC> vr, vx, oY, oR;
         if (r) vr = bv_ld<VEC>(r + (long long)n * rns + (long long)c * TV + (long long)e * VEC);
+        if (extra) vx = bv_ld<VEC>(extra + (long long)n * exns + (long long)c * TV + (long long)e * VEC);
 #pragma unroll
         for (int j = 0; j < VEC / 2; ++j) {
             const float g0 = bv_lo(vg.w[j]), g1 = bv_hi(vg.w[j]), d0 = bv_lo(vd.w[j]), d1 = bv_hi(vd.w[j]);
+            const float x0 = extra ? bv_lo(vx.w[j]) : 0.f, x1 = extra ? bv_hi(vx.w[j]) : 0.f;
             oY.w[j] = bv_pack(g0 - d0, g1 - d1);
-            oR.w[j] = bv_pack(g0 + d0, g1 + d1);
+            oR.w[j] = bv_pack(g0 + d0 + x0, g1 + d1 + x1);
             const float y0v = bv_lo(oY.w[j]), y1v = bv_hi(oY.w[j]);
             acc[0] += y0v + y1v;
             acc[1] = fmaf(y0v, bv_lo(vy.w[j]), fmaf(y1v, bv_hi(vy.w[j]), acc[1]));
@@ -610,26 +613,28 @@ extern "C" int tamgcn_gcn_epilogue_bwd(int dtype, int N, int C, int TV, const vo
 
 extern "C" int tamgcn_gcn_mid_bwd(int dtype, int N, int C, int TV, void* G, const void* DD, void* dr,
                                   int64_t dr_nstride, const void* y0, const void* r, int64_t r_nstride, double* s1g,
-                                  double* s2g, double* s1d, double* s2d, tamgcn_stream stream) {
+                                  double* s2g, double* s1d, double* s2d, const void* extra, int64_t extra_nstride,
+                                  tamgcn_stream stream) {
     TG_REQUIRE(N > 0 && C > 0 && TV > 0 && G && DD && y0 && s1g && s2g, "gcn_mid_bwd: bad arguments");
+    TG_REQUIRE(!extra || (dr && !r), "gcn_mid_bwd: `extra` is added to the dr output of the identity-residual case only");
     TG_REQUIRE(!r || (s1d && s2d), "gcn_mid_bwd: residual BN sums missing");
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = ew_grid(N, C);
     if (dtype == TAMGCN_BF16 && !bv_disabled()) {
-        const int vw = bv_width(TV, {G, DD, dr, y0, r}, {(long long)dr_nstride, (long long)r_nstride});
+        const int vw = bv_width(TV, {G, DD, dr, y0, r, extra}, {(long long)dr_nstride, (long long)r_nstride, (long long)extra_nstride});
         if (vw > 1) {
-            if (vw == 8) gcn_mid_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride, (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d);
-            else gcn_mid_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride, (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d);
+            if (vw == 8) gcn_mid_bwd_vec_kernel<8><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride, (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d, (const bf16*)extra, extra_nstride);
+            else gcn_mid_bwd_vec_kernel<4><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride, (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d, (const bf16*)extra, extra_nstride);
             count_launch();
             return check_launch("gcn_mid_bwd");
         }
     }
     if (dtype == TAMGCN_F32)
         gcn_mid_bwd_kernel<float><<<grid, 256, 0, st>>>(N, C, TV, (float*)G, (const float*)DD, (float*)dr, dr_nstride,
-                                                        (const float*)y0, (const float*)r, r_nstride, s1g, s2g, s1d, s2d);
+                                                        (const float*)y0, (const float*)r, r_nstride, s1g, s2g, s1d, s2d, (const float*)extra, extra_nstride);
     else if (dtype == TAMGCN_BF16)
         gcn_mid_bwd_kernel<bf16><<<grid, 256, 0, st>>>(N, C, TV, (bf16*)G, (const bf16*)DD, (bf16*)dr, dr_nstride,
-                                                       (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d);
+                                                       (const bf16*)y0, (const bf16*)r, r_nstride, s1g, s2g, s1d, s2d, (const bf16*)extra, extra_nstride);
     else return set_error("gcn_mid_bwd: bad dtype %d", dtype);
     count_launch();
     return check_launch("gcn_mid_bwd");

@@ -27,8 +27,10 @@ int check_launch(const char* what) {
     return 0;
 }
 
-static thread_local int g_wgrad_share = 100;
-int wgrad_sm_share() { return g_wgrad_share; }
+// process-wide (set by the step engine around its phases; read by launches from autograd's device threads)
+static std::atomic<int> g_wgrad_share{100}, g_main_share{100};
+int wgrad_sm_share() { return g_wgrad_share.load(std::memory_order_relaxed); }
+int main_sm_share() { return g_main_share.load(std::memory_order_relaxed); }
 
 int current_device() {
     int dev = 0;
@@ -60,8 +62,13 @@ void raise_smem_limit(const void* kernel, SmemLimit& lim, int dev, size_t bytes)
 }  // namespace tamgcn
 
 extern "C" int tamgcn_set_wgrad_sm_share(int percent) {
-    const int old = tamgcn::g_wgrad_share;
-    if (percent >= 1 && percent <= 100) tamgcn::g_wgrad_share = percent;
+    const int old = tamgcn::g_wgrad_share.load();
+    if (percent >= 1 && percent <= 100) tamgcn::g_wgrad_share.store(percent);
+    return old;
+}
+extern "C" int tamgcn_set_main_sm_share(int percent) {
+    const int old = tamgcn::g_main_share.load();
+    if (percent >= 1 && percent <= 100) tamgcn::g_main_share.store(percent);
     return old;
 }
 extern "C" int tamgcn_version(void) { return 100; }

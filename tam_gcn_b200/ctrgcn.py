@@ -237,6 +237,9 @@ class TCN_GCN_unit(nn.Module):
             y = self.tcn1(y)
             r = self.residual(x)
             return torch.relu(y + r)
+        # the residual's cotangent w.r.t. x is handed to gcn1's backward (same input x) instead of an autograd add pass
+        self.gcn1.__dict__.pop('_tamgcn_res_cot', None)            # nothing may be left over from an aborted backward
+        self.tcn1.__dict__['_tamgcn_res_sink'] = self.gcn1 if (self.res_kind != 'none' and x.requires_grad) else None
         return self.tcn1._run(y, x if self.res_kind != 'none' else None, self.res_kind,
                               self.residual if self.res_kind == 'conv' else None, True)
 

@@ -38,6 +38,7 @@ class Trainer:
         self.cuda = self.device.type == 'cuda'
         self.mom = torch.zeros_like(self.store.P)
         self.lr = torch.full((1,), float(lr), device=self.device, dtype=torch.float32)
+        self._one = torch.ones((), device=self.device, dtype=torch.float32)     # seed of backward (no fill kernel per step)
         self.momentum, self.nesterov, self.weight_decay = float(momentum), bool(nesterov), float(weight_decay)
         self.loss_fn = loss_fn or Fn.cross_entropy
         self.use_graph = use_graph and self.cuda
@@ -48,6 +49,8 @@ class Trainer:
         self.side = torch.cuda.Stream(device=self.device) if (self.cuda and side_stream) else None
         import os
         self.wgrad_sm_share = int(wgrad_sm_share or os.environ.get('TAMGCN_WGRAD_SM_SHARE', 50))
+        self.bwd_main_sm_share = int(os.environ.get('TAMGCN_BWD_MAIN_SM_SHARE', 100)) if self.side is not None else 100
+        self.branch_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)] if (self.cuda and side_stream) else None
         self.overlap = bool(overlap_allreduce) and self.world > 1 and self.cuda
         self.graph = None
         self.static_x = self.static_y = self.static_loss = None
@@ -135,10 +138,12 @@ class Trainer:
         self._pending = None
         self._armed = self.overlap and self._split is not None
         try:
-            with _arena.use(self.arena), st.direct_grads(), ops.side_stream(self.side, self.wgrad_sm_share):
+            with _arena.use(self.arena), st.direct_grads(), ops.side_stream(self.side, self.wgrad_sm_share), \
+                    ops.branches(self.branch_streams):
                 out = self.model(x)
                 loss = self.loss_fn(out, y)
-                loss.backward()
+                with ops.main_sm_share(self.bwd_main_sm_share):
+                    loss.backward(self._one if loss.dtype == torch.float32 and loss.dim() == 0 else None)
             ops.join_side_stream(self.side)
             if self.world > 1:
                 self._allreduce_grads()

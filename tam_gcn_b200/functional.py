@@ -332,6 +332,28 @@ def ctrgc_params(c):
 
 
 # ------------------------------------------------------------------------------------------------
+# residual cotangent hand-over inside a TCN_GCN_unit
+# ------------------------------------------------------------------------------------------------
+# out = relu(tcn1(gcn1(x)) + residual(x)): x receives a cotangent from gcn1 AND one from the residual.  Left to autograd
+# the two are summed by an ATen add over the whole activation.  Instead MsTcnFn.backward (which autograd always runs
+# before the UnitGcnFn.backward of the same unit: tcn1 consumes gcn1's output) parks the residual cotangent on the gcn1
+# module, keyed by the input it belongs to, and UnitGcnFn.backward adds it inside its last kernel.
+def _park_residual_cotangent(gcn_mod, key, dr):
+    """key = (data_ptr, version) of the residual source tensor == the unit_gcn input"""
+    gcn_mod.__dict__.setdefault('_tamgcn_res_cot', {})[key] = dr
+
+
+def _take_residual_cotangent(gcn_mod, x):
+    d = gcn_mod.__dict__.get('_tamgcn_res_cot')
+    if not d:
+        return None
+    dr = d.pop((x.data_ptr(), x._version), None)
+    if dr is not None and (dr.shape != x.shape or dr.dtype != x.dtype):
+        raise RuntimeError('residual cotangent does not match the unit_gcn input')
+    return dr
+
+
+# ------------------------------------------------------------------------------------------------
 # unit_gcn
 # ------------------------------------------------------------------------------------------------
 def unit_gcn_params(mod):
@@ -365,18 +387,20 @@ class UnitGcnFn(torch.autograd.Function):
         count = N * T * V
         KC = K * Cout
 
-        # x1 / x2: 1x1 convs on the T-mean of x
         m = _empty((N, Cin, 1, V), x, torch.float32)
-        ops.mean_t(x, m)
         x12 = _empty((N, 2 * K * R, 1, V), x, torch.float32)
-        ops.conv_fwd(m, W12, b12, x12)
-        # conv3 of the K subsets (+ down conv) in one pass over x
         Cw = KC + (Cout if has_down else 0)
         xw = _empty((N, Cw, T, V), x)
         stats = _zeros((6, Cout), x, torch.float64) if (tr_g or tr_o or tr_d) else None
         # rows: down(sum,sq), bn(sum,sq), offset(sum,sq)
         pk3 = _pack(W3, 1, x)
+        # x1 / x2: 1x1 convs on the T-mean of x — independent of conv3, on a parallel branch inside an engine step
+        with ops.branch(1):
+            ops.mean_t(x, m)
+            ops.conv_fwd(m, W12, b12, x12)
+        # conv3 of the K subsets (+ down conv) in one pass over x
         ops.conv_fwd(x, W3, b3, xw, stats=(stats[0], stats[1]) if tr_d else None, stat_c0=KC, wpack=pk3[0])
+        ops.branch_join()
         # fused topology refinement + aggregation (+ BN statistics of y0)
         y0 = _empty((N, Cout, T, V), x)
         ops.ctrgc_fwd(xw[:, :KC], x12[:, :K * R], x12[:, K * R:], W4, b4, PA, alpha, y0,
@@ -390,16 +414,19 @@ class UnitGcnFn(torch.autograd.Function):
             if has_down:
                 _bn_forward([mod.down[1]], [_full(Cout)], cd, (stats[0], stats[1]) if tr_d else None, count, tr_d)
             _bn_forward([mod.bn], [_full(Cout)], cg, (stats[2], stats[3]) if tr_g else None, count, tr_g)
-        # offset branch: z = W_o (res - y) + b_o, with res - y formed while loading
-        nsg = -cg.scale
+        # offset branch: z = W_o (res - y) + b_o, with res - y formed while loading; its coefficients
+        # (-scale_y, shift_res - shift_y) come from one tiny kernel
+        dc = torch.empty(2, Cout, device=x.device, dtype=torch.float32)
+        nsg, dsh = dc[0], dc[1]
+        ops.coef_diff(cg.scale, cd.shift if has_down else None, cg.shift, nsg, dsh)
         if has_down:
-            diff = Opnd(xw[:, KC:], y0, a=cd.scale, b=nsg, c=cd.shift - cg.shift)
+            diff = Opnd(xw[:, KC:], y0, a=cd.scale, b=nsg, c=dsh)
             res_mode, r, sr, hr = RES_AFFINE, xw[:, KC:], cd.scale, cd.shift
         elif mod.residual_identity:
-            diff = Opnd(x, y0, a=None, b=nsg, c=-cg.shift)
+            diff = Opnd(x, y0, a=None, b=nsg, c=dsh)
             res_mode, r, sr, hr = RES_IDENTITY, x, None, None
         else:
-            diff = Opnd(y0, None, a=nsg, c=-cg.shift)
+            diff = Opnd(y0, None, a=nsg, c=dsh)
             res_mode, r, sr, hr = RES_NONE, None, None, None
         oc = mod.offset_conv[0]
         Wo, bo = _w2(oc), _bias(oc, x)
@@ -435,6 +462,9 @@ class UnitGcnFn(torch.autograd.Function):
             g = g.to(x.dtype)
         go = _GradOut(x)
         sb = _zeros((6, Cout), x, torch.float64)      # rows: offset(s1,s2), bn(s1,s2), down(s1,s2)
+        # cotangent that TCN_GCN_unit's residual sends to the same input x (handed over by MsTcnFn.backward, which always
+        # runs first): folded into this backward's last kernel instead of an autograd add pass
+        xdr = _take_residual_cotangent(mod, x)
 
         # tail: ReLU mask, tanh', BN_o backward sums
         G = _empty(g.shape, x)
@@ -459,7 +489,8 @@ class UnitGcnFn(torch.autograd.Function):
             dres = None
         elif res_mode == RES_IDENTITY:
             dres = _empty(g.shape, x)
-            ops.gcn_mid_bwd(G, DD, dres, y0, None, sb[2], sb[3], None, None)
+            ops.gcn_mid_bwd(G, DD, dres, y0, None, sb[2], sb[3], None, None, extra=xdr)
+            xdr = None
         else:
             dres = None
             ops.gcn_mid_bwd(G, DD, None, y0, None, sb[2], sb[3], None, None)
@@ -497,7 +528,7 @@ class UnitGcnFn(torch.autograd.Function):
         dW3, db3 = go.buf(W3), go.buf(b3)
         ops.conv_wgrad(dxw_op, x, dW3, db3)
         dx = _empty(x.shape, x)
-        ops.conv_dgrad(dxw_op, W3, dx, addend=dres, bcast=dm, bcast_scale=1.0 / T, wpack=pk3d)
+        ops.conv_dgrad(dxw_op, W3, dx, addend=dres if dres is not None else xdr, bcast=dm, bcast_scale=1.0 / T, wpack=pk3d)
 
         grads = _ctrgc_unpack_grads(list(mod.convs), K, R, Cout, go, (W12, b12, W3, b3, W4, b4), dW12, db12, dW3, db3,
                                     dW4, db4)
@@ -661,6 +692,10 @@ class MsTcnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, r_in, mod, res_kind, res_mod, relu, *params):
+        # `res_sink` (set by TCN_GCN_unit through mod._tamgcn_res_sink): the unit_gcn whose input IS r_in; its backward
+        # takes over the residual cotangent (see _park_residual_cotangent)
+        ctx.res_sink = mod.__dict__.get('_tamgcn_res_sink') if r_in is not None else None
+        ctx.r_in_key = (r_in.data_ptr(), r_in._version) if r_in is not None else None
         x = _check_input(x)
         N, Cin, T, V = x.shape
         nd, Cb, s = mod.num_dil, mod.branch_channels, mod.stride
@@ -681,19 +716,20 @@ class MsTcnFn(torch.autograd.Function):
         h = _empty((N, Ch, T, V), x)
         st_h = _zeros((2, Ch), x, torch.float64) if tr_h else None
         pkh = _pack(Wh, 1, x)
-        ops.conv_fwd(x, Wh, bh, h, stats=st_h, wpack=pkh[0])
         u = _empty((N, Cout, To, V), x)
         st_u = _zeros((2, Cout), x, torch.float64) if tr_u else None
-        # strided 1x1 branch straight into its slice of u
         c3 = mod.branches[nd + 1][0]
         W3, b3 = _w2(c3), _bias(c3, x)
         pk3 = _pack(W3, 1, x)
-        ops.conv_fwd(x, W3, b3, u[:, Ch:], 1, s, 1, 0, stats=(st_u[0][Ch:], st_u[1][Ch:]) if tr_u else None,
-                     wpack=pk3[0])
+        # strided 1x1 branch straight into its slice of u: independent of the heads (parallel branch in an engine step)
+        with ops.branch(1):
+            ops.conv_fwd(x, W3, b3, u[:, Ch:], 1, s, 1, 0, stats=(st_u[0][Ch:], st_u[1][Ch:]) if tr_u else None,
+                         wpack=pk3[0])
+        ops.conv_fwd(x, Wh, bh, h, stats=st_h, wpack=pkh[0])
         ch = _BnCoef(Ch, x)
         sl = [slice(j * Cb, (j + 1) * Cb) for j in range(nb)]
         _bn_forward(head_bns, sl[:nd + 1], ch, st_h, N * T * V, tr_h)
-        geoms = []
+        geoms, keep = [], []
         for j in range(nd):
             tc = mod.branches[j][3].conv
             k, cs, d, p = _conv_geom(tc)
@@ -701,13 +737,18 @@ class MsTcnFn(torch.autograd.Function):
                 raise ValueError('MultiScale_TemporalConv: branch %d output length differs' % j)
             pkt = _pack(_w2(tc), k, x, cs)
             geoms.append((k, cs, d, p, pkt[1]))
-            ops.conv_fwd(Opnd(h[:, sl[j]], a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), _w2(tc), _bias(tc, x),
-                         u[:, sl[j]], k, cs, d, p, stats=(st_u[0][sl[j]], st_u[1][sl[j]]) if tr_u else None,
-                         wpack=pkt[0])
+            bj = _bias(tc, x)
+            keep.append((pkt, bj))
+            with ops.branch(j):                      # the temporal branches write disjoint slices of u: run side by side
+                ops.conv_fwd(Opnd(h[:, sl[j]], a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), _w2(tc), bj,
+                             u[:, sl[j]], k, cs, d, p, stats=(st_u[0][sl[j]], st_u[1][sl[j]]) if tr_u else None,
+                             wpack=pkt[0])
         if _conv_out_len(T, 3, s, 1, 1) != To:
             raise ValueError('MultiScale_TemporalConv: max-pool branch output length differs')
-        ops.maxpool_fwd(Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), u[:, sl[nd]], s,
-                        stats=(st_u[0][sl[nd]], st_u[1][sl[nd]]) if tr_u else None)
+        with ops.branch(nd):
+            ops.maxpool_fwd(Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), u[:, sl[nd]], s,
+                            stats=(st_u[0][sl[nd]], st_u[1][sl[nd]]) if tr_u else None)
+        ops.branch_join()
         cu = _BnCoef(Cout, x)
         # residual (its BatchNorm is finalized in the same launch as the branch BatchNorms)
         cr = r_raw = None
@@ -795,11 +836,14 @@ class MsTcnFn(torch.autograd.Function):
             hj = h[:, sl[j]]
             tgrads.append(_conv_wgrad_to(go, tc, dyj, Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]], relu=True), x,
                                          (k, cs, d, p)))
-            ops.conv_dgrad(dyj, _w2(tc), DH[:, sl[j]], k, cs, d, p, mask=Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]]),
-                           stats=(sh[0][sl[j]], sh[1][sl[j]]), wpack=pktd)
-        ops.maxpool_bwd(dy_op(sl[nd].start, sl[nd].stop),
-                        Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), DH[:, sl[nd]], s,
-                        stats=(sh[0][sl[nd]], sh[1][sl[nd]]))
+            with ops.branch(j):                      # disjoint slices of DH / of the statistics: side by side
+                ops.conv_dgrad(dyj, _w2(tc), DH[:, sl[j]], k, cs, d, p, mask=Opnd(hj, a=ch.scale[sl[j]], c=ch.shift[sl[j]]),
+                               stats=(sh[0][sl[j]], sh[1][sl[j]]), wpack=pktd)
+        with ops.branch(nd):
+            ops.maxpool_bwd(dy_op(sl[nd].start, sl[nd].stop),
+                            Opnd(h[:, sl[nd]], a=ch.scale[sl[nd]], c=ch.shift[sl[nd]], relu=True), DH[:, sl[nd]], s,
+                            stats=(sh[0][sl[nd]], sh[1][sl[nd]]))
+        ops.branch_join()
         bh_ = _BnBwd(Ch, x)
         _bn_backward(head_bns, sl[:nd + 1], ch, bh_, sh[0], sh[1], N * T * V, tr_h, go)
         dh = _bwd_opnd(DH, h, bh_, tr_h)
@@ -846,6 +890,10 @@ class MsTcnFn(torch.autograd.Function):
         br_ = mod.branches[nd + 1]
         grads += [g3[0], g3[1], go.ret(bu.dgamma[sl[nd + 1]], br_[1].weight), go.ret(bu.dbeta[sl[nd + 1]], br_[1].bias)]
         grads += rgrads
+        if dr is not None and ctx.res_sink is not None and ctx.needs_input_grad[1]:
+            # hand the residual cotangent to the unit_gcn backward that follows (keyed by the residual source tensor)
+            _park_residual_cotangent(ctx.res_sink, ctx.r_in_key, dr.contiguous())
+            dr = None
         return (dx, dr, None, None, None, None) + tuple(grads)
 
 

@@ -26,7 +26,60 @@ class Opnd:
 
 
 def _stream():
+    if _branch_stream is not None:
+        return _branch_stream.cuda_stream
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- parallel branches ----------------------------------------------------------------------------------------------
+# Independent kernels of one module (the branches of MultiScale_TemporalConv, the conv1/conv2 relation path next to
+# conv3 in unit_gcn) are small and latency-bound; inside `branches(streams)` (the engine's training step) the code
+# under `with branch(i):` is enqueued on extra stream i (ordered after everything already on the current stream) and
+# `branch_join()` makes the current stream wait for all of them.  Without an active `branches` context the code simply
+# runs inline on the current stream.  Rule for callers: every tensor touched inside a branch must stay referenced until
+# the `branch_join()` that follows (allocate outputs BEFORE entering the branch; torch's current stream is not changed,
+# so allocations still belong to the main stream).
+_branch_pool = None          # list of torch.cuda.Stream
+_branch_stream = None        # the stream of the branch being recorded, or None
+_branch_used = []
+
+
+@contextlib.contextmanager
+def branches(streams):
+    global _branch_pool
+    old = _branch_pool
+    _branch_pool = list(streams) if streams else None
+    try:
+        yield
+    finally:
+        branch_join()
+        _branch_pool = old
+
+
+@contextlib.contextmanager
+def branch(i):
+    """i = 0: the current stream itself; i >= 1: extra stream i - 1 (if the engine provided any)."""
+    global _branch_stream
+    if _branch_pool is None or i <= 0 or _branch_stream is not None:
+        yield
+        return
+    st = _branch_pool[(i - 1) % len(_branch_pool)]
+    st.wait_stream(torch.cuda.current_stream())
+    if st not in _branch_used:
+        _branch_used.append(st)
+    _branch_stream = st
+    try:
+        yield
+    finally:
+        _branch_stream = None
+
+
+def branch_join():
+    if _branch_used:
+        cur = torch.cuda.current_stream()
+        for st in _branch_used:
+            cur.wait_stream(st)
+        del _branch_used[:]
 
 
 # ---- side stream for work that is off the critical path of backward -------------------------------------------------
@@ -52,12 +105,28 @@ def side_stream(stream, sm_share=50):
     global _side
     old = _side
     _side = _Side(stream, sm_share) if stream is not None else None
+    old_share = _C.lib().tamgcn_set_wgrad_sm_share(int(sm_share)) if stream is not None else None
     try:
         yield
     finally:
+        if old_share is not None:
+            _C.lib().tamgcn_set_wgrad_sm_share(old_share)
         if _side is not None and _side.keep:
             join_side_stream(stream)
         _side = old
+
+
+@contextlib.contextmanager
+def main_sm_share(percent):
+    """Cap the persistent convolution forward / data-gradient kernels at `percent` of the SMs inside the context."""
+    if percent is None or percent >= 100:
+        yield
+        return
+    old = _C.lib().tamgcn_set_main_sm_share(int(percent))
+    try:
+        yield
+    finally:
+        _C.lib().tamgcn_set_main_sm_share(old)
 
 
 def join_side_stream(stream):
@@ -259,14 +328,9 @@ def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
     if sd is None:
         _C.check(_C.lib().tamgcn_conv_wgrad(*args, _stream()), 'tamgcn_conv_wgrad')
         return
-    sd.stream.wait_stream(torch.cuda.current_stream())
+    sd.stream.wait_stream(_branch_stream if _branch_stream is not None else torch.cuda.current_stream())
     sd.keep.append(_opnd_tensors(dy) + _opnd_tensors(x) + (dW, dbias))
-    # the SM share is thread-local in the library and backward runs on autograd's device thread: set it around the call
-    prev = _C.lib().tamgcn_set_wgrad_sm_share(sd.share)
-    try:
-        _C.check(_C.lib().tamgcn_conv_wgrad(*args, sd.stream.cuda_stream), 'tamgcn_conv_wgrad')
-    finally:
-        _C.lib().tamgcn_set_wgrad_sm_share(prev)
+    _C.check(_C.lib().tamgcn_conv_wgrad(*args, sd.stream.cuda_stream), 'tamgcn_conv_wgrad')
 
 
 def mean_t(x, m):
@@ -387,15 +451,24 @@ def gcn_epilogue_bwd(g, out, z, so, ho, G, DZ, s1o, s2o):
     _count('epilogues+maxpool', g.element_size() * g.numel() * 5)
 
 
-def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d):
+def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d, extra=None):
     N, Cc, T, V = G.shape
     dt = G.dtype
     drp, drns = (None, 0) if dr is None else _act(dr, dt)
     rp, rns = (None, 0) if r is None else _act(r, dt)
+    ep, ens = (None, 0) if extra is None else _act(extra, dt)
     _C.check(_C.lib().tamgcn_gcn_mid_bwd(_dt(G), N, Cc, T * V, _full(G, dt), _full(DD, dt), drp, drns, _full(y0, dt),
-                                         rp, rns, _f64(s1g, Cc), _f64(s2g, Cc), _f64(s1d), _f64(s2d), _stream()),
+                                         rp, rns, _f64(s1g, Cc), _f64(s2g, Cc), _f64(s1d), _f64(s2d), ep, ens, _stream()),
              'tamgcn_gcn_mid_bwd')
-    _count('epilogues+maxpool', G.element_size() * G.numel() * (4 + (1 if dr is not None else 0) + (1 if r is not None else 0)))
+    _count('epilogues+maxpool', G.element_size() * G.numel() * (4 + (1 if dr is not None else 0) + (1 if r is not None else 0) +
+                                                               (1 if extra is not None else 0)))
+
+
+def coef_diff(sb, ha, hb, nb, c):
+    """nb = -sb, c = (ha or 0) - hb  (per-channel fp32 coefficient rows)."""
+    Cn = sb.numel()
+    _C.check(_C.lib().tamgcn_coef_diff(Cn, _f32(sb, Cn), _f32(ha), _f32(hb, Cn), _f32(nb, Cn), _f32(c, Cn), _stream()),
+             'tamgcn_coef_diff')
 
 
 def tcn_epilogue_fwd(u, su, hu, res_mode, r, sr, hr, relu, out):

@@ -203,10 +203,15 @@ def gcn_epilogue_bwd(g, out, z, so, ho, G, DZ, s1o, s2o):
     _acc(s2o, dz * z.float())
 
 
-def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d):
+def coef_diff(sb, ha, hb, nb, c):
+    nb.copy_(-sb)
+    c.copy_((ha if ha is not None else 0) - hb)
+
+
+def gcn_mid_bwd(G, DD, dr, y0, r, s1g, s2g, s1d, s2d, extra=None):
     gv, dd = G.float(), DD.float()
     dy = (gv - dd).to(G.dtype).float()
-    drv = (gv + dd).to(G.dtype).float()
+    drv = (gv + dd + (extra.float() if extra is not None else 0)).to(G.dtype).float()
     G.copy_(dy.to(G.dtype))
     _acc(s1g, dy)
     _acc(s2g, dy * y0.float())
@@ -414,7 +419,7 @@ def feeder_nucla(raw, length, sample, view, frame_idx, bone_parent, mode, out):
 ALL = ['conv_pack_weights', 'conv_fwd', 'conv_dgrad', 'conv_wgrad', 'mean_t', 'ctrgc_fwd', 'ctrgc_bwd', 'bn_finalize', 'bn_bwd_coef',
        'gcn_epilogue_fwd', 'gcn_epilogue_bwd', 'gcn_mid_bwd', 'tcn_epilogue_fwd', 'tcn_epilogue_bwd', 'maxpool_fwd',
        'maxpool_bwd', 'graph_agg_fwd', 'graph_agg_bwd', 'data_bn_fwd', 'data_bn_bwd', 'pool_fc_fwd', 'pool_fc_bwd',
-       'softmax_ce_fwd', 'softmax_ce_bwd', 'sgd_step', 'transpose_act', 'feeder_nucla']
+       'softmax_ce_fwd', 'softmax_ce_bwd', 'sgd_step', 'transpose_act', 'feeder_nucla', 'coef_diff']
 
 
 def install(monkeypatch=None):

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib_built):
 def test_binding_covers_header(lib_built):
     from tam_gcn_b200 import _C
     bound = set(_C.SIGNATURES) | {'tamgcn_version', 'tamgcn_last_error', 'tamgcn_launch_count', 'tamgcn_conv_pack_bytes',
-                                     'tamgcn_set_wgrad_sm_share'}
+                                     'tamgcn_set_wgrad_sm_share', 'tamgcn_set_main_sm_share'}
     assert bound == set(declared_symbols())
     l = _C.lib()
     assert l.tamgcn_version() >= 100

@@ -320,8 +320,9 @@ def test_gcn_epilogues(dt, res_mode, TV):
         big = torch.zeros(N, C + 4, T, V, device='cuda', dtype=dt)
         dr = big[:, 1:1 + C] if res_mode else None
         st = torch.zeros(4, C, device='cuda', dtype=torch.float64)
+        extra = rnd(gen(81), N, C, T, V, dt=dt) if res_mode == 1 else None     # second cotangent of an identity residual
         fn(G, DD, dr, y0, r if res_mode == 2 else None, st[0], st[1], st[2] if res_mode == 2 else None,
-           st[3] if res_mode == 2 else None)
+           st[3] if res_mode == 2 else None, extra=extra)
         outs.append((G, big, st, G0))
     assert rel(outs[0][0], outs[1][0]) < tol(dt)
     if res_mode:
