@@ -73,6 +73,10 @@ typedef struct tamgcn_conv_geom {
 int64_t tamgcn_conv_pack_bytes(int Cout, int Cin, int k, int dgrad);
 int tamgcn_conv_pack_weights(const float* W, int Cout, int Cin, int k, void* wpack_fwd, void* wpack_dgrad,
                              tamgcn_stream stream);
+/* The same for many weight matrices in ONE launch (a step engine re-packs every convolution of the model right after
+ * the optimiser instead of once per layer call).  `table`: DEVICE array of njobs rows of 8 int64:
+ * {W pointer, wpack_fwd pointer or 0, wpack_dgrad pointer or 0, Cout, Cin, k, 0, 0}. */
+int tamgcn_conv_pack_weights_batched(const int64_t* table, int njobs, tamgcn_stream stream);
 /* 1 if the bf16 forward (dgrad = 0) / data-gradient (dgrad = 1) kernel of this shape reads a packed buffer, 0 if it
  * reads the fp32 weights directly (the small-channel temporal convolutions, Cin = Cout in {16, 32, 64}, k >= 2,
  * run on warp-level MMAs with the operand staged once per time block — csrc/tconv_mma.cu). */

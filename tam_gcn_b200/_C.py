@@ -45,6 +45,7 @@ GEOM = C.POINTER(ConvGeom)
 # name -> argtypes; must list every entry point of include/tamgcn.h (tests/test_cabi.py checks this)
 SIGNATURES = {
     'tamgcn_conv_pack_weights': [vp, i32, i32, i32, vp, vp, vp],
+    'tamgcn_conv_pack_weights_batched': [vp, i32, vp],
     'tamgcn_conv_needs_pack': [i32, i32, i32, i32, i32, i32],
     'tamgcn_conv_fwd': [GEOM, i32, OP, vp, vp, vp, vp, i64, vp, vp, i32, vp],
     'tamgcn_conv_dgrad': [GEOM, i32, OP, vp, vp, vp, i64, vp, i64, vp, f32, OP, vp, vp, vp],

@@ -560,9 +560,8 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
 //   fwd  : row = output channel, IC = Cin   : Wp(oc, tap*Cin + ic)  = W[oc, ic, tap]
 //   dgrad: row = input channel,  IC = Cout  : Wp(ic, tap*Cout + oc) = W[oc, ic, tap]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-pack_w2_kernel(const float* __restrict__ W, int Cout, int Cin, int k, uint4* __restrict__ wf, uint4* __restrict__ wd, int OCp_f,
-               int OCp_d) {
+__device__ __forceinline__ void pack_w2_body(const float* __restrict__ W, int Cout, int Cin, int k, uint4* __restrict__ wf,
+                                             uint4* __restrict__ wd, int OCp_f, int OCp_d, long long t0, long long tstride) {
     const int CK = Cin * k;
     for (int which = 0; which < 2; ++which) {
         uint4* dst = which ? wd : wf;
@@ -570,7 +569,7 @@ pack_w2_kernel(const float* __restrict__ W, int Cout, int Cin, int k, uint4* __r
         const int OC = which ? Cin : Cout, IC = which ? Cout : Cin;
         const int OCp = which ? OCp_d : OCp_f, KT = k * IC, nch = (KT + 63) / 64;
         const long long units = (long long)nch * OCp * 8;
-        for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+        for (long long u = t0; u < units; u += tstride) {
             const int piece = (int)(u & 7);
             const long long rowl = u >> 3;
             const int oc = (int)(rowl % OCp), ch = (int)(rowl / OCp);
@@ -592,6 +591,25 @@ pack_w2_kernel(const float* __restrict__ W, int Cout, int Cin, int k, uint4* __r
     }
 }
 
+__global__ void __launch_bounds__(256)
+pack_w2_kernel(const float* __restrict__ W, int Cout, int Cin, int k, uint4* __restrict__ wf, uint4* __restrict__ wd, int OCp_f,
+               int OCp_d) {
+    pack_w2_body(W, Cout, Cin, k, wf, wd, OCp_f, OCp_d, (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                 (long long)gridDim.x * blockDim.x);
+}
+
+// every weight matrix of a model in ONE launch: job j = blockIdx.y, table row = {W, wf, wd, Cout, Cin, k} (8 x int64)
+__global__ void __launch_bounds__(256)
+pack_w2_batched_kernel(const long long* __restrict__ table) {
+    const long long* j = table + (long long)blockIdx.y * 8;
+    const float* W = reinterpret_cast<const float*>(j[0]);
+    uint4* wf = reinterpret_cast<uint4*>(j[1]);
+    uint4* wd = reinterpret_cast<uint4*>(j[2]);
+    const int Cout = (int)j[3], Cin = (int)j[4], k = (int)j[5];
+    pack_w2_body(W, Cout, Cin, k, wf, wd, (Cout + 127) & ~127, (Cin + 127) & ~127,
+                 (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
 static bool c2_disabled() {
     static int v = -1;
     if (v < 0) {
@@ -606,6 +624,13 @@ static int oc_pad128(int OC) { return (OC + 127) & ~127; }
 size_t conv_pack_bytes(int Cout, int Cin, int k, int dgrad) {
     const int OC = dgrad ? Cin : Cout, IC = dgrad ? Cout : Cin;
     return (size_t)((k * IC + 63) / 64) * (size_t)oc_pad128(OC) * 128;
+}
+
+int conv_pack_weights_batched(const long long* table, int njobs, cudaStream_t st) {
+    dim3 grid(16, (unsigned)njobs);
+    pack_w2_batched_kernel<<<grid, 256, 0, st>>>(table);
+    count_launch();
+    return check_launch("conv_pack_weights_batched");
 }
 
 int conv_pack_weights(const float* W, int Cout, int Cin, int k, void* wf, void* wd, cudaStream_t st) {
@@ -768,6 +793,11 @@ int conv_dgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const void* wpack, 
 
 extern "C" int64_t tamgcn_conv_pack_bytes(int Cout, int Cin, int k, int dgrad) {
     return (int64_t)tamgcn::conv_pack_bytes(Cout, Cin, k, dgrad);
+}
+
+extern "C" int tamgcn_conv_pack_weights_batched(const int64_t* table, int njobs, tamgcn_stream stream) {
+    TG_REQUIRE(table && njobs > 0 && njobs <= 65535, "conv_pack_weights_batched: bad arguments (njobs=%d)", njobs);
+    return tamgcn::conv_pack_weights_batched(reinterpret_cast<const long long*>(table), njobs, (cudaStream_t)stream);
 }
 
 extern "C" int tamgcn_conv_pack_weights(const float* W, int Cout, int Cin, int k, void* wpack_fwd, void* wpack_dgrad,

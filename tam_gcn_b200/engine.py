@@ -45,6 +45,7 @@ class Trainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.pg = process_group
         self.arena = _arena.ZeroArena(self.device)
+        self.packs = ops.PackCache(model) if self.cuda else None
         self._arena_keep = []                       # buffers baked into captured graphs: never freed
         self.side = torch.cuda.Stream(device=self.device) if (self.cuda and side_stream) else None
         import os
@@ -139,7 +140,7 @@ class Trainer:
         self._armed = self.overlap and self._split is not None
         try:
             with _arena.use(self.arena), st.direct_grads(), ops.side_stream(self.side, self.wgrad_sm_share), \
-                    ops.branches(self.branch_streams):
+                    ops.branches(self.branch_streams), Fn.pack_cache(self.packs):
                 out = self.model(x)
                 loss = self.loss_fn(out, y)
                 with ops.main_sm_share(self.bwd_main_sm_share):
@@ -229,6 +230,7 @@ class Predictor:
         """eval_mode=False keeps the model in train() — the frozen-but-training GCN branch of the cross-modal fusion
         model (models/resnet_gcn_attention.py:24-26): forward only, batch statistics, running stats updated."""
         self.model = model.eval() if eval_mode else model.train()
+        self.packs = ops.PackCache(model)
         self.use_graph = use_graph
         self.graph = None
         self.static_x = self.static_out = None
@@ -238,19 +240,21 @@ class Predictor:
     def __call__(self, x):
         from . import _C
         if not self.use_graph:
-            return self.model(x)
+            with Fn.pack_cache(self.packs):
+                return self.model(x)
         if self.graph is None or self.static_x.shape != x.shape:
             self.static_x = x.clone()
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self.model(self.static_x)
+                    with Fn.pack_cache(self.packs):
+                        self.model(self.static_x)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             n0 = _C.launch_count()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph), Fn.pack_cache(self.packs):     # one batched weight-tile refresh per replay
                 self.static_out = self.model(self.static_x)
             self.captured_launches = _C.launch_count() - n0
         self.static_x.copy_(x, non_blocking=True)

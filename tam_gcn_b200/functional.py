@@ -24,6 +24,8 @@ Inside `ParamStore.direct_grads()` (the engine's training step) the kernels accu
 flat gradient buffer — the slice that mirrors the parameter (or the whole pack of adjacent parameters) — and
 autograd gets None for them; that buffer is what the optimiser kernel and the NCCL all-reduce consume.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -32,6 +34,23 @@ from .ops import Opnd, RES_NONE, RES_IDENTITY, RES_AFFINE
 
 
 _sink = None          # params.ParamStore while its direct_grads() context is active
+_pack_cache = None    # ops.PackCache of the engine driving the current step (persistent tensor-core weight tiles)
+
+
+@contextlib.contextmanager
+def pack_cache(cache):
+    """Inside the context `_pack` serves weight tiles from `cache` (refreshed by one batched launch per step)."""
+    global _pack_cache
+    old = _pack_cache
+    _pack_cache = cache
+    try:
+        if cache is not None:
+            cache.repack_all()
+        yield cache
+    finally:
+        if cache is not None:
+            cache.end_step()
+        _pack_cache = old
 
 
 # ------------------------------------------------------------------------------------------------
@@ -161,6 +180,8 @@ def _pack(W2d, k, like, stride=1):
     (and per entry for the shapes whose kernel reads the fp32 weights directly)."""
     if like.dtype != torch.bfloat16:
         return None, None
+    if _pack_cache is not None:
+        return _pack_cache.get(W2d, W2d.shape[0], W2d.shape[1] // k, k, stride, like.shape[3])
     return ops.conv_pack_weights(W2d, W2d.shape[0], W2d.shape[1] // k, k, stride, like.shape[3])
 
 

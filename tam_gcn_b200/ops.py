@@ -308,6 +308,61 @@ def conv_pack_weights(W, Cout, Cin, k, stride=1, V=0):
     return wf, wd
 
 
+class PackCache:
+    """Persistent tensor-core weight tiles of a model whose parameters change once per step (the optimiser) or never
+    (inference).  `get` hands out the same buffers for the same weight matrix; `repack_all` refreshes ALL of them in one
+    launch (tamgcn_conv_pack_weights_batched) — a step engine calls it at the start of the step, so the ~46 per-layer
+    pack launches of a CTR-GCN step become one.  Until `repack_all` has run in the current step (`fresh`), `get` packs
+    the matrix it returns itself, so a cache is never stale."""
+
+    def __init__(self, model):
+        self.model = model
+        self.storages = set()
+        self.entries = {}            # key -> (wf, wd, W)
+        self.table = None
+        self.fresh = False
+
+    def _is_parameter_memory(self, W):
+        """Only views of the model's own parameters have an address that means the same matrix next step (a torch.cat
+        of DataParallel replica weights does not)."""
+        sp = W.untyped_storage().data_ptr()
+        if sp not in self.storages:
+            self.storages = {p.untyped_storage().data_ptr() for p in self.model.parameters()}
+        return sp in self.storages
+
+    def get(self, W, Cout, Cin, k, stride, V):
+        key = (W.data_ptr(), Cout, Cin, k, stride, V, W.device)
+        e = self.entries.get(key)
+        if e is None:
+            wf, wd = conv_pack_weights(W, Cout, Cin, k, stride, V)
+            if not self._is_parameter_memory(W):
+                return wf, wd
+            self.entries[key] = (wf, wd, W)
+            self.table = None
+            return wf, wd
+        wf, wd, _ = e
+        if not self.fresh and (wf is not None or wd is not None):
+            _C.check(_C.lib().tamgcn_conv_pack_weights(_f32(W, Cout * Cin * k), Cout, Cin, k, _p(wf), _p(wd), _stream()),
+                     'tamgcn_conv_pack_weights')
+        return wf, wd
+
+    def repack_all(self):
+        jobs = [(W, wf, wd, key) for key, (wf, wd, W) in self.entries.items() if wf is not None or wd is not None]
+        if not jobs:
+            return
+        if self.table is None:
+            if jobs[0][0].is_cuda and torch.cuda.is_current_stream_capturing():
+                return                               # cannot build the table now: `get` keeps packing per call
+            rows = [[W.data_ptr(), _p(wf) or 0, _p(wd) or 0, key[1], key[2], key[3], 0, 0] for W, wf, wd, key in jobs]
+            self.table = torch.tensor(rows, dtype=torch.int64).to(jobs[0][0].device)
+        _C.check(_C.lib().tamgcn_conv_pack_weights_batched(self.table.data_ptr(), self.table.shape[0], _stream()),
+                 'tamgcn_conv_pack_weights_batched')
+        self.fresh = True
+
+    def end_step(self):
+        self.fresh = False
+
+
 def conv_wgrad(dy, x, dW, dbias, k=1, stride=1, dil=1, pad=0):
     """dW += dY (*) X, dbias += sum dY  (fp32 accumulators, zeroed by the caller).  Runs on the side stream when one
     is active (see `side_stream`)."""

@@ -417,3 +417,37 @@ def test_errors_are_loud():
                       torch.zeros(1, 17, 17, device='cuda'), torch.ones(1, device='cuda'), torch.zeros_like(x))
     with pytest.raises(RuntimeError, match='CUDA'):
         ops.mean_t(torch.zeros(1, 2, 3, 20), torch.zeros(1, 2, 1, 20))
+
+
+def test_batched_weight_pack_matches_per_matrix_pack():
+    """tamgcn_conv_pack_weights_batched (one launch for a whole model) writes the same tiles as one
+    tamgcn_conv_pack_weights call per matrix, and PackCache serves them without re-packing once fresh."""
+    dev = _dev()
+    import torch.nn as nn
+    from tam_gcn_b200 import _C, ops
+    torch.manual_seed(3)
+    shapes = [(64, 3, 1), (128, 64, 5), (256, 128, 1), (40, 24, 9), (64, 64, 3)]
+    model = nn.ParameterList([nn.Parameter(torch.randn(co, ci * k, device=dev)) for co, ci, k in shapes])
+    cache = ops.PackCache(model)
+    ref = []
+    for W, (co, ci, k) in zip(model, shapes):
+        ref.append(ops.conv_pack_weights(W, co, ci, k))
+        cache.get(W, co, ci, k, 1, 0)
+    assert len(cache.entries) == len(shapes)
+    with torch.no_grad():
+        for W in model:
+            W.mul_(-0.5)
+    ref = [ops.conv_pack_weights(W, co, ci, k) for W, (co, ci, k) in zip(model, shapes)]
+    cache.repack_all()
+    n0 = _C.launch_count()
+    for W, (co, ci, k), (rf, rd) in zip(model, shapes, ref):
+        wf, wd = cache.get(W, co, ci, k, 1, 0)
+        assert torch.equal(wf, rf) and torch.equal(wd, rd)
+    assert _C.launch_count() == n0                   # fresh: no per-matrix launch
+    cache.end_step()
+    cache.get(model[0], *shapes[0], 1, 0)
+    assert _C.launch_count() == n0 + 1               # not fresh: the matrix handed out is re-packed
+    # a matrix that is not parameter memory is packed but never cached
+    tmp = torch.randn(32, 16, device=dev)
+    cache.get(tmp, 32, 16, 1, 1, 0)
+    assert len(cache.entries) == len(shapes)
