@@ -385,7 +385,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
 //   dQ[u,v]    = sum_t g[t,u] x3[t,v]           per channel, operands re-distributed with movmatrix
 //   raw[c,r]   = sum_uv dQ[c,uv] D[r,uv]        (row R of D is all ones: raw[c,R] = sum_uv dQ)  -> dW4, db4, dalpha
 //   dD[r,uv]   = sum_c W4[c,r] dQ[c,uv]         -> dS = alpha dD (1 - D^2) -> dx1, dx2
-template <int V>
+// LEAN (large R: the full tables do not fit 227 KB): the fp32 tanh table is not kept — the last phase recomputes
+// tanh from x1/x2 (same instruction, same value) and stages dS for 16 rows of r at a time.
+template <int V, bool LEAN>
 __global__ void __launch_bounds__(CBM_THREADS)
 ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float* __restrict__ x1,
                      const float* __restrict__ x2, const float* __restrict__ W4, const float* __restrict__ b4,
@@ -399,8 +401,8 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
     const int R = g.R, K = g.K, Tn = g.T;
     const int Rp = (R + 15) & ~15, RW = Rp + 8;          // K extent of the r contraction, pitch of W4b rows
     const int NR = R + 1, NRt = (NR + 7) / 8, DR = NRt * 8 > Rp ? NRt * 8 : Rp;   // rows of Db (R data rows, ones row, zero rows)
-    float* Df = smem;                                   // [R][UVp]     tanh table, later dS
-    float* dQs = Df + (size_t)R * UVp;                  // [CT][UV]     fp32 dQ (for dPA)
+    float* Df = smem;                                   // [R][UVp]     tanh table, later dS   (LEAN: [16][UVp], dS only)
+    float* dQs = Df + (size_t)(LEAN ? 16 : R) * UVp;    // [CT][UV]     fp32 dQ (for dPA)
     float* b4s = dQs + CT * UV;                         // [CT]
     float* x12s = b4s + CT;                             // [2][R*V]
     float* red = x12s + 2 * R * V;                      // [64]
@@ -450,7 +452,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                 const float a = x12s[r * V + u];
                 const float4 b = *reinterpret_cast<const float4*>(x12s + R * V + r * V + v);
                 const float4 d = make_float4(tanh_fast(a - b.x), tanh_fast(a - b.y), tanh_fast(a - b.z), tanh_fast(a - b.w));
-                *reinterpret_cast<float4*>(Df + (size_t)r * UVp + 4 * q) = d;
+                if (!LEAN) *reinterpret_cast<float4*>(Df + (size_t)r * UVp + 4 * q) = d;
                 *reinterpret_cast<uint2*>(Db + (size_t)r * UP + 4 * q) = make_uint2(pack2_bf16(d.x, d.y), pack2_bf16(d.z, d.w));
             }
         } else {
@@ -461,7 +463,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                     const int u = uv / V, v = uv - u * V;
                     d = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]);
                 }
-                Df[idx] = d;
+                if (!LEAN) Df[idx] = d;
                 Db[r * UP + uv] = __float2bfloat16_rn(d);
             }
         }
@@ -655,67 +657,270 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
             }
         }
         // ---- dD[r,uv] = sum_c W4[c,r] dQ[c,uv];  dS = alpha dD (1 - D^2) overwrites the tanh table ----
-        for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
-            uint32_t b0, b1;
-            ldsm_x2_trans(b0, b1, dQc + (size_t)(lane & 15) * UP + nt * 8);
-            for (int mt = 0; mt < Rp / 16; ++mt) {
-                const bf16* wa = W4T + (mt * 16 + gid) * 24 + 2 * tig;
-                const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(wa), *reinterpret_cast<const uint32_t*>(wa + 8 * 24),
-                                       *reinterpret_cast<const uint32_t*>(wa + 8), *reinterpret_cast<const uint32_t*>(wa + 8 * 24 + 8)};
-                float d[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_bf16_16816(d, a, b0, b1);
+        // ---- dx1[r,u] += sum_v dS[r,u,v];  dx2[r,v] -= sum_u dS[r,u,v] ----
+        const int MT = Rp / 16;
+        for (int pass = 0; pass < (LEAN ? MT : 1); ++pass) {
+            const int mt_lo = LEAN ? pass : 0, mt_hi = LEAN ? pass + 1 : MT;
+            const int r_lo = mt_lo * 16, r_n = min(R, mt_hi * 16) - r_lo;       // rows staged in Df this pass
+            for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
+                uint32_t b0, b1;
+                ldsm_x2_trans(b0, b1, dQc + (size_t)(lane & 15) * UP + nt * 8);
+                const int uv = nt * 8 + 2 * tig;
+                int u0 = 0, v0 = 0, u1 = 0, v1 = 0;
+                if (LEAN) { u0 = uv / V; v0 = uv - u0 * V; u1 = (uv + 1) / V; v1 = uv + 1 - u1 * V; }
+                for (int mt = mt_lo; mt < mt_hi; ++mt) {
+                    const bf16* wa = W4T + (mt * 16 + gid) * 24 + 2 * tig;
+                    const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(wa), *reinterpret_cast<const uint32_t*>(wa + 8 * 24),
+                                           *reinterpret_cast<const uint32_t*>(wa + 8), *reinterpret_cast<const uint32_t*>(wa + 8 * 24 + 8)};
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};
+                    mma_bf16_16816(d, a, b0, b1);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = mt * 16 + gid + 8 * h, uv = nt * 8 + 2 * tig;
-                    if (r < R) {
-                        float2* pd = reinterpret_cast<float2*>(Df + (size_t)r * UVp + uv);
-                        const float2 dv = *pd;
-                        *pd = make_float2(alpha * d[2 * h] * (1.f - dv.x * dv.x), alpha * d[2 * h + 1] * (1.f - dv.y * dv.y));
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = mt * 16 + gid + 8 * h;
+                        if (r < R) {
+                            float2* pd = reinterpret_cast<float2*>(Df + (size_t)(r - r_lo) * UVp + uv);
+                            float2 dv;
+                            if (LEAN) {
+                                dv.x = uv < UV ? tanh_fast(x12s[r * V + u0] - x12s[R * V + r * V + v0]) : 0.f;
+                                dv.y = uv + 1 < UV ? tanh_fast(x12s[r * V + u1] - x12s[R * V + r * V + v1]) : 0.f;
+                            } else {
+                                dv = *pd;
+                            }
+                            *pd = make_float2(alpha * d[2 * h] * (1.f - dv.x * dv.x), alpha * d[2 * h + 1] * (1.f - dv.y * dv.y));
+                        }
                     }
                 }
             }
-        }
-        __syncthreads();
-        // ---- dx1[r,u] += sum_v dS[r,u,v];  dx2[r,v] -= sum_u dS[r,u,v] ----
-        if (V % 4 == 0) {
-            // 16-byte shared-memory loads: a dx1 task sums one row of V values, a dx2 task four adjacent columns
-            constexpr int QU = V / 4;
-            for (int task = tid; task < R * V; task += CBM_THREADS) {
-                const int r = task / V, u = task - r * V;
-                const float4* ds = reinterpret_cast<const float4*>(Df + (size_t)r * UVp + u * V);
-                float s = 0.f;
+            __syncthreads();
+            if (V % 4 == 0) {
+                // 16-byte shared-memory loads: a dx1 task sums one row of V values, a dx2 task four adjacent columns
+                constexpr int QU = V / 4;
+                for (int task = tid; task < r_n * V; task += CBM_THREADS) {
+                    const int rl = task / V, u = task - rl * V, r = r_lo + rl;
+                    const float4* ds = reinterpret_cast<const float4*>(Df + (size_t)rl * UVp + u * V);
+                    float s = 0.f;
 #pragma unroll
-                for (int o = 0; o < QU; ++o) { const float4 d = ds[o]; s += (d.x + d.y) + (d.z + d.w); }
-                atomicAdd(dx1 + (long long)n * g.x12ns + (i * R + r) * V + u, s);
-            }
-            for (int task = tid; task < R * QU; task += CBM_THREADS) {
-                const int r = task / QU, vq = task - r * QU;
-                const float* ds = Df + (size_t)r * UVp + 4 * vq;
-                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 5
-                for (int o = 0; o < V; ++o) {
-                    const float4 d = *reinterpret_cast<const float4*>(ds + o * V);
-                    s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+                    for (int o = 0; o < QU; ++o) { const float4 d = ds[o]; s += (d.x + d.y) + (d.z + d.w); }
+                    atomicAdd(dx1 + (long long)n * g.x12ns + (i * R + r) * V + u, s);
                 }
-                float* dst = dx2 + (long long)n * g.x12ns + (i * R + r) * V + 4 * vq;
-                atomicAdd(dst, -s.x); atomicAdd(dst + 1, -s.y); atomicAdd(dst + 2, -s.z); atomicAdd(dst + 3, -s.w);
-            }
-        } else {
-            for (int task = tid; task < 2 * R * V; task += CBM_THREADS) {
-                const int which = task / (R * V), rem = task - which * R * V, r = rem / V, w = rem - r * V;
-                const float* ds = Df + (size_t)r * UVp + (which ? w : w * V);
-                const int step = which ? V : 1;
-                float s = 0.f;
+                for (int task = tid; task < r_n * QU; task += CBM_THREADS) {
+                    const int rl = task / QU, vq = task - rl * QU, r = r_lo + rl;
+                    const float* ds = Df + (size_t)rl * UVp + 4 * vq;
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 5
-                for (int o = 0; o < V; ++o) s += ds[o * step];
-                float* dst = (which ? dx2 : dx1) + (long long)n * g.x12ns + (i * R + r) * V + w;
-                atomicAdd(dst, which ? -s : s);
+                    for (int o = 0; o < V; ++o) {
+                        const float4 d = *reinterpret_cast<const float4*>(ds + o * V);
+                        s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+                    }
+                    float* dst = dx2 + (long long)n * g.x12ns + (i * R + r) * V + 4 * vq;
+                    atomicAdd(dst, -s.x); atomicAdd(dst + 1, -s.y); atomicAdd(dst + 2, -s.z); atomicAdd(dst + 3, -s.w);
+                }
+            } else {
+                for (int task = tid; task < 2 * r_n * V; task += CBM_THREADS) {
+                    const int which = task / (r_n * V), rem = task - which * r_n * V, rl = rem / V, w = rem - rl * V;
+                    const int r = r_lo + rl;
+                    const float* ds = Df + (size_t)rl * UVp + (which ? w : w * V);
+                    const int step = which ? V : 1;
+                    float s = 0.f;
+#pragma unroll 5
+                    for (int o = 0; o < V; ++o) s += ds[o * step];
+                    float* dst = (which ? dx2 : dx1) + (long long)n * g.x12ns + (i * R + r) * V + w;
+                    atomicAdd(dst, which ? -s : s);
+                }
             }
+            if (LEAN) __syncthreads();
         }
     }
     float dv[1] = {dalpha_acc};
     block_sum<1>(dv, red);
     if (tid == 0) atomicAdd(dalpha, dv[0]);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// forward on warp-level tensor-core MMAs (bf16): the shapes the tcgen05 kernels (ctrgc_tc*.cu) do not cover — large R,
+// where their fp16 tanh table no longer fits next to the pipeline stages (NTU l6-l10: V = 25, R = 16 / 32).
+//   Q_i[c,uv]  = alpha (sum_r W4_i[c,r] D_i[r,uv] + b4_i[c]) + PA_i[uv]     m16n8k16, M = 16 channels of the CTA
+//   y[t,u]     = sum_i sum_v x3_i[t,v] Q_i[u,v]                             per channel (one warp each), A fragments
+//                                                                           straight from global memory
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(CBM_THREADS)
+ctrgc_fwd_mma_kernel(CtrgcP g, const bf16* __restrict__ x3, const float* __restrict__ x1, const float* __restrict__ x2,
+                     const float* __restrict__ W4, const float* __restrict__ b4, const float* __restrict__ PA,
+                     const float* __restrict__ alpha_p, bf16* __restrict__ y, double* ssum, double* ssq) {
+    constexpr int CT = CBM_CT;
+    constexpr int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8;
+    constexpr int NTn = (V + 7) / 8;          // 8-wide u / v tiles (20 -> 3, 25 -> 4)
+    constexpr int QP = 40;                    // pitch (bf16) of a Q row: 32 v + 8 padding (conflict-free fragment reads)
+    extern __shared__ __align__(16) float smem[];
+    const int R = g.R, K = g.K, Tn = g.T;
+    const int Rp = (R + 15) & ~15, RW = Rp + 8;
+    float* x12s = smem;                                 // [2][R*V]
+    float* b4s = x12s + 2 * R * V;                      // [CT]
+    bf16* Db = reinterpret_cast<bf16*>(b4s + CT);       // [Rp][UP]   tanh table of the current subset
+    bf16* W4b = Db + (size_t)Rp * UP;                   // [16][RW]
+    bf16* Qn = W4b + 16 * RW;                           // [K][CT][8*NTn][QP]   Q[i][c][u][v]
+    const int n = blockIdx.y, c0 = blockIdx.x * CT;
+    const int nc = min(CT, g.Cout - c0);
+    const float alpha = __ldg(alpha_p);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const long long TV = (long long)Tn * V;
+    const bf16 zero = __float2bfloat16_rn(0.f);
+
+    for (int idx = tid; idx < K * CT * 8 * NTn * QP / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Qn)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    for (int idx = tid; idx < Rp * UP / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Db)[idx] = make_uint4(0u, 0u, 0u, 0u);
+
+    for (int i = 0; i < K; ++i) {
+        __syncthreads();
+        for (int idx = tid; idx < R * V; idx += CBM_THREADS) {
+            x12s[idx] = __ldg(x1 + (long long)n * g.x12ns + i * R * V + idx);
+            x12s[R * V + idx] = __ldg(x2 + (long long)n * g.x12ns + i * R * V + idx);
+        }
+        for (int idx = tid; idx < 16 * RW; idx += CBM_THREADS) {
+            const int c = idx / RW, r = idx - c * RW;
+            W4b[idx] = (c < nc && r < R) ? __float2bfloat16_rn(__ldg(W4 + ((long long)i * g.Cout + c0 + c) * R + r)) : zero;
+        }
+        for (int idx = tid; idx < CT; idx += CBM_THREADS) b4s[idx] = idx < nc ? __ldg(b4 + i * g.Cout + c0 + idx) : 0.f;
+        __syncthreads();
+        if (V % 4 == 0) {
+            constexpr int QR = UVp / 4, QU = V / 4;
+            for (int idx = tid; idx < R * QR; idx += CBM_THREADS) {
+                const int r = idx / QR, q = idx - r * QR, u = q / QU, v = 4 * (q - u * QU);
+                const float a = x12s[r * V + u];
+                const float4 b = *reinterpret_cast<const float4*>(x12s + R * V + r * V + v);
+                *reinterpret_cast<uint2*>(Db + (size_t)r * UP + 4 * q) =
+                    make_uint2(pack2_bf16(tanh_fast(a - b.x), tanh_fast(a - b.y)), pack2_bf16(tanh_fast(a - b.z), tanh_fast(a - b.w)));
+            }
+        } else {
+            // two consecutive uv per step (UV odd: the last pair is half padding)
+            for (int idx = tid; idx < R * (UVp / 2); idx += CBM_THREADS) {
+                const int r = idx / (UVp / 2), uv = 2 * (idx - r * (UVp / 2));
+                float d0 = 0.f, d1 = 0.f;
+                if (uv < UV) { const int u = uv / V, v = uv - u * V; d0 = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]); }
+                if (uv + 1 < UV) { const int u = (uv + 1) / V, v = uv + 1 - u * V; d1 = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]); }
+                *reinterpret_cast<uint32_t*>(Db + (size_t)r * UP + uv) = pack2_bf16(d0, d1);
+            }
+        }
+        __syncthreads();
+        bf16* Qi = Qn + (size_t)i * CT * 8 * NTn * QP;
+        for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            const int uv0 = nt * 8 + 2 * tig;
+            const float pa0 = uv0 < UV ? __ldg(PA + i * UV + uv0) : 0.f;
+            const float pa1 = uv0 + 1 < UV ? __ldg(PA + i * UV + uv0 + 1) : 0.f;
+            for (int ks = 0; ks < Rp / 16; ++ks) {
+                const bf16* wa = W4b + gid * RW + ks * 16 + 2 * tig;
+                const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(wa), *reinterpret_cast<const uint32_t*>(wa + 8 * RW),
+                                       *reinterpret_cast<const uint32_t*>(wa + 8), *reinterpret_cast<const uint32_t*>(wa + 8 * RW + 8)};
+                uint32_t b0, b1;
+                ldsm_x2_trans(b0, b1, Db + (size_t)(ks * 16 + (lane & 15)) * UP + nt * 8);
+                mma_bf16_16816(d, a, b0, b1);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = gid + 8 * (e >> 1), uv = nt * 8 + 2 * tig + (e & 1);
+                if (c < nc && uv < UV) {
+                    const int u = uv / V, v = uv - u * V;
+                    Qi[(c * 8 * NTn + u) * QP + v] = __float2bfloat16_rn(fmaf(alpha, d[e] + b4s[c], (e & 1) ? pa1 : pa0));
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    if (warp < nc) {
+        const int c = warp;
+        const bf16* xp0 = x3 + (long long)n * g.x3ns + (long long)(c0 + c) * TV;
+        bf16* yp = y + (long long)n * g.yns + (long long)(c0 + c) * TV;
+        const bool fastld = (V % 2 == 0) && ((reinterpret_cast<uintptr_t>(x3) & 3) == 0) && ((g.x3ns & 1) == 0);
+        float s1 = 0.f, s2 = 0.f;
+        for (int t0 = 0; t0 < Tn; t0 += 16) {
+            float acc[NTn][4];
+#pragma unroll
+            for (int nt = 0; nt < NTn; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+            for (int i = 0; i < K; ++i) {
+                const bf16* xp = xp0 + (long long)i * g.Cout * TV;
+                uint32_t xa[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = t0 + gid + 8 * h;
+                    const bool tok = t < Tn;
+                    const long long ro = (long long)t * V;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int v = 8 * b + 2 * tig;
+                        if (fastld) xa[h][b] = (tok && v < V) ? __ldg(reinterpret_cast<const unsigned*>(xp + ro + v)) : 0u;
+                        else xa[h][b] = ld_pair(xp, ro + v, tok && v < V, v + 1 < V);
+                    }
+                }
+                const bf16* qt = Qn + ((size_t)i * CT + c) * 8 * NTn * QP;
+#pragma unroll
+                for (int nt = 0; nt < NTn; ++nt) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const bf16* q0 = qt + (nt * 8 + gid) * QP + ks * 16 + 2 * tig;
+                        const uint32_t a[4] = {xa[0][2 * ks], xa[1][2 * ks], xa[0][2 * ks + 1], xa[1][2 * ks + 1]};
+                        mma_bf16_16816(acc[nt], a, *reinterpret_cast<const uint32_t*>(q0), *reinterpret_cast<const uint32_t*>(q0 + 8));
+                    }
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTn; ++nt) {
+                const int u = 8 * nt + 2 * tig;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = t0 + gid + 8 * h;
+                    const bool ok = t < Tn && u < V, ok1 = u + 1 < V;
+                    const uint32_t w = pack2_bf16(acc[nt][2 * h], acc[nt][2 * h + 1]);
+                    if (ok) {
+                        const float lo = __uint_as_float(w << 16), hi = ok1 ? __uint_as_float(w & 0xffff0000u) : 0.f;
+                        s1 += lo + hi;
+                        s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                    }
+                    st_pair(yp, (long long)t * V + u, w, ok, ok1);
+                }
+            }
+        }
+        if (ssum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+            if (lane == 0) { atomicAdd(ssum + c0 + c, (double)s1); atomicAdd(ssq + c0 + c, (double)s2); }
+        }
+    }
+}
+
+static size_t ctrgc_fwd_mma_smem(int V, int R, int K) {
+    const int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8, NTn = (V + 7) / 8;
+    const int Rp = (R + 15) & ~15, RW = Rp + 8;
+    return sizeof(float) * (2 * (size_t)R * V + CBM_CT) +
+           sizeof(bf16) * ((size_t)Rp * UP + 16 * (size_t)RW + (size_t)K * CBM_CT * 8 * NTn * 40) + 16;
+}
+
+// returns 1 if launched, 0 if the shape does not fit (caller falls back to the SIMT kernel), <0 on error
+static int launch_fwd_mma(const CtrgcP& g0, int V, const void* x3, const float* x1, const float* x2, const float* W4,
+                          const float* b4, const float* PA, const float* alpha, void* y, double* ssum, double* ssq,
+                          cudaStream_t st) {
+    static const bool off = [] { const char* e = getenv("TAMGCN_DISABLE_FWD_MMA"); return e && e[0] == '1'; }();
+    if (off) return 0;
+    CtrgcP g = g0;
+    g.CT = CBM_CT;
+    const size_t sm = ctrgc_fwd_mma_smem(V, g.R, g.K);
+    if (sm > 227 * 1024 || (g.R * V) % 2) return 0;
+    dim3 grid(cdiv(g.Cout, g.CT), g.N);
+    if (V == 20) {
+        static SmemLimit lim;
+        ensure_smem(ctrgc_fwd_mma_kernel<20>, lim, sm);
+        ctrgc_fwd_mma_kernel<20><<<grid, CBM_THREADS, sm, st>>>(g, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)y, ssum, ssq);
+    } else {
+        static SmemLimit lim;
+        ensure_smem(ctrgc_fwd_mma_kernel<25>, lim, sm);
+        ctrgc_fwd_mma_kernel<25><<<grid, CBM_THREADS, sm, st>>>(g, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)y, ssum, ssq);
+    }
+    count_launch();
+    const int rc = check_launch("ctrgc_fwd(mma)");
+    return rc < 0 ? rc : 1;
 }
 
 template <typename T>
@@ -742,10 +947,10 @@ static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, c
     return check_launch("ctrgc_fwd");
 }
 
-static size_t ctrgc_bwd_mma_smem(int V, int R) {
+static size_t ctrgc_bwd_mma_smem(int V, int R, bool lean) {
     const int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8, NTn = (V + 7) / 8;
     const int Rp = (R + 15) & ~15, RW = Rp + 8, NRt = (R + 1 + 7) / 8, DR = NRt * 8 > Rp ? NRt * 8 : Rp;
-    return sizeof(float) * ((size_t)R * UVp + (size_t)CBM_CT * UV + CBM_CT + 2 * (size_t)R * V + 64) +
+    return sizeof(float) * ((size_t)(lean ? 16 : R) * UVp + (size_t)CBM_CT * UV + CBM_CT + 2 * (size_t)R * V + 64) +
            sizeof(bf16) * ((size_t)DR * UP + 16 * (size_t)UP + 16 * RW + (size_t)Rp * 24 + (size_t)CBM_CT * 8 * NTn * 40) + 16;
 }
 
@@ -755,20 +960,22 @@ static int launch_bwd_mma(const CtrgcP& g0, int V, const Opnd& go, const void* x
                           float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha, cudaStream_t st) {
     CtrgcP g = g0;
     g.CT = CBM_CT;
-    const size_t sm = ctrgc_bwd_mma_smem(V, g.R);
+    static const int lean_env = [] { const char* e = getenv("TAMGCN_CBM_LEAN"); return e ? atoi(e) : 0; }();   // 1: force
+    bool lean = lean_env == 1 && g.R > 16;
+    size_t sm = ctrgc_bwd_mma_smem(V, g.R, lean);
+    if (sm > 227 * 1024 && g.R > 16) { lean = true; sm = ctrgc_bwd_mma_smem(V, g.R, true); }
     if (sm > 227 * 1024 || g.R > 128 || (g.R & 1)) return 0;
     dim3 grid(cdiv(g.Cout, g.CT), g.N);
-    if (V == 20) {
-        static SmemLimit lim;
-        ensure_smem(ctrgc_bwd_mma_kernel<20>, lim, sm);
-        ctrgc_bwd_mma_kernel<20><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns,
-                                                                dx1, dx2, dW4, db4, dPA, dalpha);
-    } else {
-        static SmemLimit lim;
-        ensure_smem(ctrgc_bwd_mma_kernel<25>, lim, sm);
-        ctrgc_bwd_mma_kernel<25><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)dx3, dx3ns,
-                                                                dx1, dx2, dW4, db4, dPA, dalpha);
-    }
+#define CBM_LAUNCH(VV, LL)                                                                                                  \
+    do {                                                                                                                    \
+        static SmemLimit lim;                                                                                               \
+        ensure_smem(ctrgc_bwd_mma_kernel<VV, LL>, lim, sm);                                                                 \
+        ctrgc_bwd_mma_kernel<VV, LL><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha,       \
+                                                                    (bf16*)dx3, dx3ns, dx1, dx2, dW4, db4, dPA, dalpha);   \
+    } while (0)
+    if (V == 20) { if (lean) CBM_LAUNCH(20, true); else CBM_LAUNCH(20, false); }
+    else         { if (lean) CBM_LAUNCH(25, true); else CBM_LAUNCH(25, false); }
+#undef CBM_LAUNCH
     count_launch();
     const int rc = check_launch("ctrgc_bwd(mma)");
     return rc < 0 ? rc : 1;
@@ -858,6 +1065,10 @@ extern "C" int tamgcn_ctrgc_fwd(int dtype, const void* x3, int64_t x3_nstride, i
         if (rc != 0) return rc < 0 ? rc : 0;
     }
     if (dtype == TAMGCN_F32) return launch_fwd<float>(g, V, x3, x1, x2, W4, b4, PA, alpha, y, stat_sum, stat_sumsq, st);
+    if (dtype == TAMGCN_BF16) {     // warp-MMA kernel for what the tcgen05 kernels leave (large R)
+        const int rc = launch_fwd_mma(g, V, x3, x1, x2, W4, b4, PA, alpha, y, stat_sum, stat_sumsq, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     if (dtype == TAMGCN_BF16) return launch_fwd<bf16>(g, V, x3, x1, x2, W4, b4, PA, alpha, y, stat_sum, stat_sumsq, st);
     return set_error("ctrgc_fwd: bad dtype %d", dtype);
 }

@@ -190,7 +190,9 @@ CTRGC_CFG = [(20, 64, 8, 12, 3), (20, 24, 8, 52, 3), (25, 64, 16, 10, 3), (25, 4
              (25, 64, 8, 64, 3), (20, 10, 8, 70, 3), (20, 128, 16, 26, 3), (20, 6, 8, 5, 1), (25, 7, 8, 33, 2),
              (20, 64, 8, 52, 3), (20, 8, 8, 40, 3), (20, 12, 8, 33, 2), (20, 4, 8, 64, 1), (20, 256, 8, 34, 3),
              # V = 25, R = 8, 32 < T <= 64, T % 8 == 0: ctrgc_tc4.cu
-             (25, 128, 8, 48, 3), (25, 8, 8, 40, 2), (25, 64, 8, 56, 1), (25, 4, 8, 64, 3)]
+             (25, 128, 8, 48, 3), (25, 8, 8, 40, 2), (25, 64, 8, 56, 1), (25, 4, 8, 64, 3),
+             # V = 25, R > 16: the backward's staged (LEAN) variant
+             (25, 256, 32, 16, 3), (25, 48, 24, 9, 2)]
 
 
 def _ctrgc_inputs(g, dt, V, Cout, R, T, K, N=3):
