@@ -18,6 +18,14 @@ if len(sys.argv) > 2 and sys.argv[2] == 'l6_64':
     N, Cout, T, V, K, R = 64, 128, 26, 20, 3, 16
 if len(sys.argv) > 2 and sys.argv[2] == 'l9_64':
     N, Cout, T, V, K, R = 64, 256, 13, 20, 3, 32
+if len(sys.argv) > 2 and sys.argv[2] == 'ntu_l6':
+    N, Cout, T, V, K, R = 512, 128, 32, 25, 3, 16
+if len(sys.argv) > 2 and sys.argv[2] == 'ntu_l8':
+    N, Cout, T, V, K, R = 512, 256, 32, 25, 3, 16
+if len(sys.argv) > 2 and sys.argv[2] == 'ntu_l9':
+    N, Cout, T, V, K, R = 512, 256, 16, 25, 3, 32
+if len(sys.argv) > 2 and sys.argv[2] == 'ntu_l9_64':
+    N, Cout, T, V, K, R = 64, 256, 16, 25, 3, 32
 dev = 'cuda'
 g = torch.Generator(device='cuda').manual_seed(0)
 x3 = torch.randn(N, K * Cout, T, V, device=dev, generator=g).to(dtype)

@@ -740,162 +740,290 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
 // ------------------------------------------------------------------------------------------------
 // forward on warp-level tensor-core MMAs (bf16): the shapes the tcgen05 kernels (ctrgc_tc*.cu) do not cover — large R,
 // where their fp16 tanh table no longer fits next to the pipeline stages (NTU l6-l10: V = 25, R = 16 / 32).
-//   Q_i[c,uv]  = alpha (sum_r W4_i[c,r] D_i[r,uv] + b4_i[c]) + PA_i[uv]     m16n8k16, M = 16 channels of the CTA
-//   y[t,u]     = sum_i sum_v x3_i[t,v] Q_i[u,v]                             per channel (one warp each), A fragments
-//                                                                           straight from global memory
+//   Q_i[c,uv]  = alpha (sum_r W4_i[c,r] D_i[r,uv] + b4_i[c]) + PA_i[uv]     m16n8k16, M = 16 channels of a tile
+//   y[t,u]     = sum_i sum_v x3_i[t,v] Q_i[u,v]                             per channel (one warp each)
+// A CTA owns one sample and every S-th 16-channel tile: the tanh tables of all K subsets are built ONCE per CTA
+// (bf16, shared memory) and reused by all its tiles.  Steps j = (tile, subset): the x3 rows of step j+1 stream into a
+// per-warp staging buffer with cp.async while step j computes; with two Q buffers (NQ = 2) the Q build of step j+1
+// and the contraction of step j share one barrier interval.
 // ------------------------------------------------------------------------------------------------
-template <int V>
-__global__ void __launch_bounds__(CBM_THREADS)
-ctrgc_fwd_mma_kernel(CtrgcP g, const bf16* __restrict__ x3, const float* __restrict__ x1, const float* __restrict__ x2,
-                     const float* __restrict__ W4, const float* __restrict__ b4, const float* __restrict__ PA,
-                     const float* __restrict__ alpha_p, bf16* __restrict__ y, double* ssum, double* ssq) {
+struct CfmP {
+    int S;            // channel-tile stride (gridDim.x)
+    int NQ;           // Q buffers (1 or 2)
+    int cpw;          // cp.async width in bytes for x3 (16 / 8 / 4)
+    int yw;           // copy-out width in bytes for y (16 / 8 / 4 / 2)
+    int xs_bytes;     // staging bytes per warp and buffer
+};
+
+__device__ __forceinline__ void cfm_cp_async(uint32_t dst, const void* src, int w) {
+    if (w == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else if (w == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+#define CFM_KS 2      // R <= 32
+
+template <int V, int TB>
+__global__ void __launch_bounds__(CBM_THREADS, 1)
+ctrgc_fwd_mma_kernel(CtrgcP g, CfmP f, const bf16* __restrict__ x3, const float* __restrict__ x1,
+                     const float* __restrict__ x2, const float* __restrict__ W4, const float* __restrict__ b4,
+                     const float* __restrict__ PA, const float* __restrict__ alpha_p, bf16* __restrict__ y, double* ssum,
+                     double* ssq) {
     constexpr int CT = CBM_CT;
     constexpr int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8;
     constexpr int NTn = (V + 7) / 8;          // 8-wide u / v tiles (20 -> 3, 25 -> 4)
     constexpr int QP = 40;                    // pitch (bf16) of a Q row: 32 v + 8 padding (conflict-free fragment reads)
+    constexpr int CQ = 8 * NTn * QP + 8;      // channel stride of a Q buffer (+8: the build's stores of 8 channels hit 8 bank groups)
+    constexpr int QSZ = CT * CQ;              // one Q buffer (bf16 elements)
     extern __shared__ __align__(16) float smem[];
     const int R = g.R, K = g.K, Tn = g.T;
-    const int Rp = (R + 15) & ~15, RW = Rp + 8;
-    float* x12s = smem;                                 // [2][R*V]
-    float* b4s = x12s + 2 * R * V;                      // [CT]
-    bf16* Db = reinterpret_cast<bf16*>(b4s + CT);       // [Rp][UP]   tanh table of the current subset
-    bf16* W4b = Db + (size_t)Rp * UP;                   // [16][RW]
-    bf16* Qn = W4b + 16 * RW;                           // [K][CT][8*NTn][QP]   Q[i][c][u][v]
-    const int n = blockIdx.y, c0 = blockIdx.x * CT;
-    const int nc = min(CT, g.Cout - c0);
+    const int Rp = (R + 15) & ~15, KS = Rp / 16;
+    bf16* Db = reinterpret_cast<bf16*>(smem);                               // [K][Rp][UP]  tanh tables
+    bf16* Qn = Db + (size_t)K * Rp * UP;                                    // [NQ][CT][CQ]  Q[c][u][v]
+    unsigned char* xs = reinterpret_cast<unsigned char*>(Qn + (size_t)f.NQ * QSZ);   // [2][16 warps][xs_bytes]
+    float* x12s = reinterpret_cast<float*>(xs + 2 * 16 * (size_t)f.xs_bytes);        // [2][R*V]  (table build only)
+    const int n = blockIdx.y;
     const float alpha = __ldg(alpha_p);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const long long TV = (long long)Tn * V;
-    const bf16 zero = __float2bfloat16_rn(0.f);
+    const int nTiles = (g.Cout + CT - 1) / CT;
+    const int myTiles = (nTiles - (int)blockIdx.x + f.S - 1) / f.S;
+    const int J = myTiles * K;
 
-    for (int idx = tid; idx < K * CT * 8 * NTn * QP / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Qn)[idx] = make_uint4(0u, 0u, 0u, 0u);
-    for (int idx = tid; idx < Rp * UP / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Db)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    // padding rows / columns of Q and D stay zero: only valid entries are ever rewritten
+    for (int idx = tid; idx < f.NQ * QSZ / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Qn)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    for (int idx = tid; idx < K * Rp * UP / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Db)[idx] = make_uint4(0u, 0u, 0u, 0u);
 
+    // x3 rows of step j (this warp's channel) -> staging buffer j & 1
+    const uint32_t xs_s = (uint32_t)__cvta_generic_to_shared(xs);
+    const int row_bytes = (int)TV * 2;
+    int sj_tile = (int)blockIdx.x, sj_i = 0;             // (tile, subset) of the next step to stage
+    auto stage = [&](int j) {
+        if (j < J) {
+            const int c = sj_tile * CT + warp;
+            if (c < g.Cout) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(x3 + (long long)n * g.x3ns + ((long long)sj_i * g.Cout + c) * TV);
+                const uint32_t dst = xs_s + (uint32_t)((j & 1) * 16 + warp) * (uint32_t)f.xs_bytes;
+                for (int o = lane * f.cpw; o < row_bytes; o += 32 * f.cpw) cfm_cp_async(dst + o, src + o, f.cpw);
+            }
+            if (++sj_i == K) { sj_i = 0; sj_tile += f.S; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0);
+
+    // ---- tanh tables of all subsets ----
     for (int i = 0; i < K; ++i) {
         __syncthreads();
         for (int idx = tid; idx < R * V; idx += CBM_THREADS) {
             x12s[idx] = __ldg(x1 + (long long)n * g.x12ns + i * R * V + idx);
             x12s[R * V + idx] = __ldg(x2 + (long long)n * g.x12ns + i * R * V + idx);
         }
-        for (int idx = tid; idx < 16 * RW; idx += CBM_THREADS) {
-            const int c = idx / RW, r = idx - c * RW;
-            W4b[idx] = (c < nc && r < R) ? __float2bfloat16_rn(__ldg(W4 + ((long long)i * g.Cout + c0 + c) * R + r)) : zero;
-        }
-        for (int idx = tid; idx < CT; idx += CBM_THREADS) b4s[idx] = idx < nc ? __ldg(b4 + i * g.Cout + c0 + idx) : 0.f;
         __syncthreads();
-        if (V % 4 == 0) {
-            constexpr int QR = UVp / 4, QU = V / 4;
-            for (int idx = tid; idx < R * QR; idx += CBM_THREADS) {
-                const int r = idx / QR, q = idx - r * QR, u = q / QU, v = 4 * (q - u * QU);
-                const float a = x12s[r * V + u];
-                const float4 b = *reinterpret_cast<const float4*>(x12s + R * V + r * V + v);
-                *reinterpret_cast<uint2*>(Db + (size_t)r * UP + 4 * q) =
-                    make_uint2(pack2_bf16(tanh_fast(a - b.x), tanh_fast(a - b.y)), pack2_bf16(tanh_fast(a - b.z), tanh_fast(a - b.w)));
-            }
-        } else {
-            // two consecutive uv per step (UV odd: the last pair is half padding)
-            for (int idx = tid; idx < R * (UVp / 2); idx += CBM_THREADS) {
-                const int r = idx / (UVp / 2), uv = 2 * (idx - r * (UVp / 2));
-                float d0 = 0.f, d1 = 0.f;
-                if (uv < UV) { const int u = uv / V, v = uv - u * V; d0 = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]); }
-                if (uv + 1 < UV) { const int u = (uv + 1) / V, v = uv + 1 - u * V; d1 = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]); }
-                *reinterpret_cast<uint32_t*>(Db + (size_t)r * UP + uv) = pack2_bf16(d0, d1);
-            }
-        }
-        __syncthreads();
-        bf16* Qi = Qn + (size_t)i * CT * 8 * NTn * QP;
-        for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-            const int uv0 = nt * 8 + 2 * tig;
-            const float pa0 = uv0 < UV ? __ldg(PA + i * UV + uv0) : 0.f;
-            const float pa1 = uv0 + 1 < UV ? __ldg(PA + i * UV + uv0 + 1) : 0.f;
-            for (int ks = 0; ks < Rp / 16; ++ks) {
-                const bf16* wa = W4b + gid * RW + ks * 16 + 2 * tig;
-                const uint32_t a[4] = {*reinterpret_cast<const uint32_t*>(wa), *reinterpret_cast<const uint32_t*>(wa + 8 * RW),
-                                       *reinterpret_cast<const uint32_t*>(wa + 8), *reinterpret_cast<const uint32_t*>(wa + 8 * RW + 8)};
-                uint32_t b0, b1;
-                ldsm_x2_trans(b0, b1, Db + (size_t)(ks * 16 + (lane & 15)) * UP + nt * 8);
-                mma_bf16_16816(d, a, b0, b1);
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = gid + 8 * (e >> 1), uv = nt * 8 + 2 * tig + (e & 1);
-                if (c < nc && uv < UV) {
-                    const int u = uv / V, v = uv - u * V;
-                    Qi[(c * 8 * NTn + u) * QP + v] = __float2bfloat16_rn(fmaf(alpha, d[e] + b4s[c], (e & 1) ? pa1 : pa0));
-                }
-            }
+        bf16* Di = Db + (size_t)i * Rp * UP;
+        for (int idx = tid; idx < R * (UVp / 2); idx += CBM_THREADS) {
+            const int r = idx / (UVp / 2), uv = 2 * (idx - r * (UVp / 2));
+            float d0 = 0.f, d1 = 0.f;
+            if (uv < UV) { const int u = uv / V, v = uv - u * V; d0 = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]); }
+            if (uv + 1 < UV) { const int u = (uv + 1) / V, v = uv + 1 - u * V; d1 = tanh_fast(x12s[r * V + u] - x12s[R * V + r * V + v]); }
+            *reinterpret_cast<uint32_t*>(Di + (size_t)r * UP + uv) = pack2_bf16(d0, d1);
         }
     }
     __syncthreads();
 
-    if (warp < nc) {
-        const int c = warp;
-        const bf16* xp0 = x3 + (long long)n * g.x3ns + (long long)(c0 + c) * TV;
-        bf16* yp = y + (long long)n * g.yns + (long long)(c0 + c) * TV;
-        const bool fastld = (V % 2 == 0) && ((reinterpret_cast<uintptr_t>(x3) & 3) == 0) && ((g.x3ns & 1) == 0);
-        float s1 = 0.f, s2 = 0.f;
-        for (int t0 = 0; t0 < Tn; t0 += 16) {
-            float acc[NTn][4];
+    // A fragments of the Q build (W4 rows of a tile's 16 channels, bf16) straight from global memory, requested one
+    // phase before their use
+    uint32_t afr[CFM_KS][4];
+    float b4a = 0.f, b4b = 0.f;
+    int bq_tile = (int)blockIdx.x, bq_i = 0;             // (tile, subset) of the next Q build
+    auto load_w4 = [&](int j) {
+        if (j >= J) return;
+        const int c0 = bq_tile * CT, ca = c0 + gid, cb = c0 + gid + 8;
+        const bool oka = ca < g.Cout, okb = cb < g.Cout;
+        const float* wa = W4 + ((long long)bq_i * g.Cout + ca) * R;
+        const float* wb = W4 + ((long long)bq_i * g.Cout + cb) * R;
+        b4a = oka ? __ldg(b4 + bq_i * g.Cout + ca) : 0.f;
+        b4b = okb ? __ldg(b4 + bq_i * g.Cout + cb) : 0.f;
 #pragma unroll
-            for (int nt = 0; nt < NTn; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-            for (int i = 0; i < K; ++i) {
-                const bf16* xp = xp0 + (long long)i * g.Cout * TV;
-                uint32_t xa[2][4];
+        for (int ks = 0; ks < CFM_KS; ++ks) {
+            const int r0 = ks * 16 + 2 * tig;
+            float w[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int t = t0 + gid + 8 * h;
-                    const bool tok = t < Tn;
-                    const long long ro = (long long)t * V;
+            for (int q = 0; q < 4; ++q) {
+                const int r = r0 + (q & 1) + 8 * (q >> 1);
+                w[q] = (oka && r < R) ? __ldg(wa + r) : 0.f;
+                w[4 + q] = (okb && r < R) ? __ldg(wb + r) : 0.f;
+            }
+            afr[ks][0] = pack2_bf16(w[0], w[1]);
+            afr[ks][1] = pack2_bf16(w[4], w[5]);
+            afr[ks][2] = pack2_bf16(w[2], w[3]);
+            afr[ks][3] = pack2_bf16(w[6], w[7]);
+        }
+    };
+    // Q of the step whose fragments load_w4 fetched last, into buffer Qb
+    auto build_q = [&](bf16* Qb) {
+        const int i = bq_i, c0 = bq_tile * CT;
+        if (++bq_i == K) { bq_i = 0; bq_tile += f.S; }
+        const bf16* Di = Db + (size_t)i * Rp * UP;
+        const bool oka = c0 + gid < g.Cout, okb = c0 + gid + 8 < g.Cout;
+        bf16* qa = Qb + gid * CQ;
+        bf16* qb = qa + 8 * CQ;
+        const float* pa = PA + i * UV;
+        // (u, v) of this lane's first accumulator column, advanced by 16 tiles = 128 columns per iteration
+        int uv = warp * 8 + 2 * tig;
+        int u = uv / V, v = uv - u * V;
+        constexpr int DU = 128 / V, DV = 128 - DU * V;
+        for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            const float pa0 = uv < UV ? __ldg(pa + uv) : 0.f;
+            const float pa1 = uv + 1 < UV ? __ldg(pa + uv + 1) : 0.f;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int v = 8 * b + 2 * tig;
-                        if (fastld) xa[h][b] = (tok && v < V) ? __ldg(reinterpret_cast<const unsigned*>(xp + ro + v)) : 0u;
-                        else xa[h][b] = ld_pair(xp, ro + v, tok && v < V, v + 1 < V);
-                    }
+            for (int ks = 0; ks < CFM_KS; ++ks) {
+                if (ks < KS) {
+                    uint32_t b0, b1;
+                    ldsm_x2_trans(b0, b1, Di + (size_t)(ks * 16 + (lane & 15)) * UP + nt * 8);
+                    mma_bf16_16816(d, afr[ks], b0, b1);
                 }
-                const bf16* qt = Qn + ((size_t)i * CT + c) * 8 * NTn * QP;
+            }
+            const int o0 = u * QP + v;
+            int o1 = o0 + 1;
+            if (v + 1 == V) o1 = o0 + QP - (V - 1);
+            if (uv < UV) {
+                if (oka) qa[o0] = __float2bfloat16_rn(fmaf(alpha, d[0] + b4a, pa0));
+                if (okb) qb[o0] = __float2bfloat16_rn(fmaf(alpha, d[2] + b4b, pa0));
+            }
+            if (uv + 1 < UV) {
+                if (oka) qa[o1] = __float2bfloat16_rn(fmaf(alpha, d[1] + b4a, pa1));
+                if (okb) qb[o1] = __float2bfloat16_rn(fmaf(alpha, d[3] + b4b, pa1));
+            }
+            uv += 128; u += DU; v += DV;
+            if (v >= V) { v -= V; ++u; }
+        }
+    };
+
+    float acc[TB][NTn][4];
+    float s1 = 0.f, s2 = 0.f;
+    // element e = t*V + v of this lane's first fragment word (t = gid, v = 2*tig); every other word of the lane is an
+    // even number of elements further, so the word offset and the half-word shift are per-lane constants
+    const int e0 = gid * V + 2 * tig;
+    const int sh = (V % 2) ? (e0 & 1) * 16 : 0;
+    int ct_tile = (int)blockIdx.x, ct_i = 0;             // (tile, subset) of the next contraction
+    // contraction of step j: x3 fragments from the staging buffer, Q fragments from Qb
+    auto contract = [&](int j, const bf16* Qb) {
+        const int i = ct_i, c = ct_tile * CT + warp;
+        if (++ct_i == K) { ct_i = 0; ct_tile += f.S; }
+        if (i == 0) {
+#pragma unroll
+            for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+                for (int nt = 0; nt < NTn; ++nt) acc[tb][nt][0] = acc[tb][nt][1] = acc[tb][nt][2] = acc[tb][nt][3] = 0.f;
+        }
+        if (c >= g.Cout) return;
+        unsigned char* xb = xs + (size_t)((j & 1) * 16 + warp) * f.xs_bytes;
+        const uint32_t* xw = reinterpret_cast<const uint32_t*>(xb) + (e0 >> 1);
+        uint32_t xa[TB][2][4];
+#pragma unroll
+        for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool tok = tb * 16 + gid + 8 * h < Tn;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int wo = ((tb * 16 + 8 * h) * V + 8 * b) / 2;         // compile-time word offset
+                    uint32_t w = 0u;
+                    if (8 * b + 2 * tig < V && tok) {
+                        if (V % 2 == 0) w = xw[wo];
+                        else w = __funnelshift_r(xw[wo], xw[wo + 1], sh);
+                        if (8 * b + 2 * tig + 1 >= V) w &= 0xffffu;
+                    }
+                    xa[tb][h][b] = w;
+                }
+            }
+        const bf16* qt = Qb + (size_t)warp * CQ;
+#pragma unroll
+        for (int nt = 0; nt < NTn; ++nt) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const bf16* q0 = qt + (nt * 8 + gid) * QP + ks * 16 + 2 * tig;
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(q0), b1 = *reinterpret_cast<const uint32_t*>(q0 + 8);
+#pragma unroll
+                for (int tb = 0; tb < TB; ++tb) {
+                    const uint32_t a[4] = {xa[tb][0][2 * ks], xa[tb][1][2 * ks], xa[tb][0][2 * ks + 1], xa[tb][1][2 * ks + 1]};
+                    mma_bf16_16816(acc[tb][nt], a, b0, b1);
+                }
+            }
+        }
+        if (i == K - 1) {
+            // the finished (channel, all t) block has the layout of the staging buffer: written there, copied out in
+            // wide coalesced words
+            __syncwarp();
+            s1 = 0.f; s2 = 0.f;
+            unsigned short* xh = reinterpret_cast<unsigned short*>(xb);
+#pragma unroll
+            for (int tb = 0; tb < TB; ++tb)
 #pragma unroll
                 for (int nt = 0; nt < NTn; ++nt) {
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const bf16* q0 = qt + (nt * 8 + gid) * QP + ks * 16 + 2 * tig;
-                        const uint32_t a[4] = {xa[0][2 * ks], xa[1][2 * ks], xa[0][2 * ks + 1], xa[1][2 * ks + 1]};
-                        mma_bf16_16816(acc[nt], a, *reinterpret_cast<const uint32_t*>(q0), *reinterpret_cast<const uint32_t*>(q0 + 8));
+                    for (int h = 0; h < 2; ++h) {
+                        const bool ok = (tb * 16 + gid + 8 * h < Tn) && 8 * nt + 2 * tig < V, ok1 = 8 * nt + 2 * tig + 1 < V;
+                        const uint32_t w = pack2_bf16(acc[tb][nt][2 * h], acc[tb][nt][2 * h + 1]);
+                        if (ok) {
+                            const float lo = __uint_as_float(w << 16), hi = ok1 ? __uint_as_float(w & 0xffff0000u) : 0.f;
+                            s1 += lo + hi;
+                            s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+                            const int e = e0 + (tb * 16 + 8 * h) * V + 8 * nt;
+                            xh[e] = (unsigned short)(w & 0xffffu);
+                            if (ok1) xh[e + 1] = (unsigned short)(w >> 16);
+                        }
                     }
                 }
+            __syncwarp();
+            unsigned char* yp = reinterpret_cast<unsigned char*>(y + (long long)n * g.yns + (long long)c * TV);
+            if (f.yw == 16) {
+                for (int o = lane * 16; o < row_bytes; o += 512) *reinterpret_cast<uint4*>(yp + o) = *reinterpret_cast<const uint4*>(xb + o);
+            } else if (f.yw == 8) {
+                for (int o = lane * 8; o < row_bytes; o += 256) *reinterpret_cast<uint2*>(yp + o) = *reinterpret_cast<const uint2*>(xb + o);
+            } else if (f.yw == 4) {
+                for (int o = lane * 4; o < row_bytes; o += 128) *reinterpret_cast<uint32_t*>(yp + o) = *reinterpret_cast<const uint32_t*>(xb + o);
+            } else {
+                for (int o = lane * 2; o < row_bytes; o += 64) *reinterpret_cast<unsigned short*>(yp + o) = *reinterpret_cast<const unsigned short*>(xb + o);
             }
+            if (ssum) {
 #pragma unroll
-            for (int nt = 0; nt < NTn; ++nt) {
-                const int u = 8 * nt + 2 * tig;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int t = t0 + gid + 8 * h;
-                    const bool ok = t < Tn && u < V, ok1 = u + 1 < V;
-                    const uint32_t w = pack2_bf16(acc[nt][2 * h], acc[nt][2 * h + 1]);
-                    if (ok) {
-                        const float lo = __uint_as_float(w << 16), hi = ok1 ? __uint_as_float(w & 0xffff0000u) : 0.f;
-                        s1 += lo + hi;
-                        s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
-                    }
-                    st_pair(yp, (long long)t * V + u, w, ok, ok1);
-                }
+                for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+                if (lane == 0) { atomicAdd(ssum + c, (double)s1); atomicAdd(ssq + c, (double)s2); }
             }
         }
-        if (ssum) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-            if (lane == 0) { atomicAdd(ssum + c0 + c, (double)s1); atomicAdd(ssq + c0 + c, (double)s2); }
+    };
+
+    if (f.NQ == 2) {
+        load_w4(0);
+        build_q(Qn);
+        __syncthreads();
+        for (int j = 0; j < J; ++j) {
+            stage(j + 1);
+            load_w4(j + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            contract(j, Qn + (size_t)(j & 1) * QSZ);
+            if (j + 1 < J) build_q(Qn + (size_t)((j + 1) & 1) * QSZ);
+            __syncthreads();
+        }
+    } else {
+        load_w4(0);
+        for (int j = 0; j < J; ++j) {
+            stage(j + 1);
+            build_q(Qn);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncthreads();
+            load_w4(j + 1);
+            contract(j, Qn);
+            __syncthreads();
         }
     }
-}
-
-static size_t ctrgc_fwd_mma_smem(int V, int R, int K) {
-    const int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8, NTn = (V + 7) / 8;
-    const int Rp = (R + 15) & ~15, RW = Rp + 8;
-    return sizeof(float) * (2 * (size_t)R * V + CBM_CT) +
-           sizeof(bf16) * ((size_t)Rp * UP + 16 * (size_t)RW + (size_t)K * CBM_CT * 8 * NTn * 40) + 16;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // returns 1 if launched, 0 if the shape does not fit (caller falls back to the SIMT kernel), <0 on error
@@ -906,18 +1034,49 @@ static int launch_fwd_mma(const CtrgcP& g0, int V, const void* x3, const float* 
     if (off) return 0;
     CtrgcP g = g0;
     g.CT = CBM_CT;
-    const size_t sm = ctrgc_fwd_mma_smem(V, g.R, g.K);
-    if (sm > 227 * 1024 || (g.R * V) % 2) return 0;
-    dim3 grid(cdiv(g.Cout, g.CT), g.N);
-    if (V == 20) {
-        static SmemLimit lim;
-        ensure_smem(ctrgc_fwd_mma_kernel<20>, lim, sm);
-        ctrgc_fwd_mma_kernel<20><<<grid, CBM_THREADS, sm, st>>>(g, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)y, ssum, ssq);
-    } else {
-        static SmemLimit lim;
-        ensure_smem(ctrgc_fwd_mma_kernel<25>, lim, sm);
-        ctrgc_fwd_mma_kernel<25><<<grid, CBM_THREADS, sm, st>>>(g, (const bf16*)x3, x1, x2, W4, b4, PA, alpha, (bf16*)y, ssum, ssq);
+    if (g.T > 64 || g.R > 16 * CFM_KS) return 0;                       // accumulators of all T live in registers
+    const long long TVb = (long long)g.T * V * 2;
+    if (TVb % 4) return 0;
+    const uintptr_t xa = (uintptr_t)x3;
+    CfmP f;
+    f.cpw = (TVb % 16 == 0 && (g.x3ns * 2) % 16 == 0 && (xa & 15) == 0) ? 16
+          : ((TVb % 8 == 0 && (g.x3ns * 2) % 8 == 0 && (xa & 7) == 0) ? 8 : (((g.x3ns * 2) % 4 == 0 && (xa & 3) == 0) ? 4 : 0));
+    if (f.cpw == 0) return 0;
+    const uintptr_t ya = (uintptr_t)y;
+    f.yw = (TVb % 16 == 0 && (g.yns * 2) % 16 == 0 && (ya & 15) == 0) ? 16
+         : ((TVb % 8 == 0 && (g.yns * 2) % 8 == 0 && (ya & 7) == 0) ? 8 : (((g.yns * 2) % 4 == 0 && (ya & 3) == 0) ? 4 : 2));
+    f.xs_bytes = (int)((TVb + 15) & ~15LL) + 16;
+    const int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8, NTn = (V + 7) / 8;
+    const int Rp = (g.R + 15) & ~15;
+    const size_t szD = sizeof(bf16) * (size_t)g.K * Rp * UP, szQ = sizeof(bf16) * (size_t)CBM_CT * (8 * NTn * 40 + 8);
+    const size_t szX = 2 * 16 * (size_t)f.xs_bytes, szP = sizeof(float) * 2 * (size_t)g.R * V;
+    f.NQ = (szD + 2 * szQ + szX + szP + 16 <= 227 * 1024) ? 2 : 1;
+    const size_t sm = szD + f.NQ * szQ + szX + szP + 16;
+    if (sm > 227 * 1024) return 0;
+    // channel-tile stride S: waves(S) * (table cost + tiles per CTA * tile cost), table : tile ~ R : 16
+    const int nTiles = cdiv(g.Cout, CBM_CT);
+    int S = 1;
+    {
+        double best = 1e30;
+        for (int c = 1; c <= nTiles && c <= 16; ++c) {
+            const double waves = (double)cdiv((long long)g.N * c, num_sms());
+            const double cost = waves * ((double)g.R / 16.0 + (double)cdiv(nTiles, c));
+            if (cost < best - 1e-9) { best = cost; S = c; }
+        }
     }
+    f.S = S;
+    dim3 grid(S, g.N);
+#define CFM_LAUNCH(VV, TT)                                                                                                  \
+    do {                                                                                                                    \
+        static SmemLimit lim;                                                                                               \
+        ensure_smem(ctrgc_fwd_mma_kernel<VV, TT>, lim, sm);                                                                 \
+        ctrgc_fwd_mma_kernel<VV, TT><<<grid, CBM_THREADS, sm, st>>>(g, f, (const bf16*)x3, x1, x2, W4, b4, PA, alpha,       \
+                                                                    (bf16*)y, ssum, ssq);                                   \
+    } while (0)
+    const int TB = g.T <= 16 ? 1 : (g.T <= 32 ? 2 : 4);
+    if (V == 20) { if (TB == 1) CFM_LAUNCH(20, 1); else if (TB == 2) CFM_LAUNCH(20, 2); else CFM_LAUNCH(20, 4); }
+    else         { if (TB == 1) CFM_LAUNCH(25, 1); else if (TB == 2) CFM_LAUNCH(25, 2); else CFM_LAUNCH(25, 4); }
+#undef CFM_LAUNCH
     count_launch();
     const int rc = check_launch("ctrgc_fwd(mma)");
     return rc < 0 ? rc : 1;
