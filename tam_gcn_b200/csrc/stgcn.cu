@@ -161,6 +161,12 @@ graph_agg_dA_kernel(int N, int K, int C, int Tn, int V, Opnd go, const T* __rest
     }
 }
 
+// bf16 tensor-core versions (stgcn_mma.cu): 1 = launched, 0 = not covered, < 0 = error
+int graph_agg_fwd_mma(int N, int K, int C, int T, int V, const void* y, long long yns, const float* A, void* out,
+                      long long ons, double* ssum, double* ssq, cudaStream_t st);
+int graph_agg_bwd_mma(int N, int K, int C, int T, int V, const Opnd& go, const void* y, long long yns, const float* A,
+                      void* dy, long long dyns, float* dA, cudaStream_t st);
+
 }  // namespace tamgcn
 
 using namespace tamgcn;
@@ -172,6 +178,10 @@ extern "C" int tamgcn_graph_agg_fwd(int dtype, int N, int K, int C, int T, int V
     TG_REQUIRE(V == 20 || V == 25, "graph_agg_fwd: V=%d not supported (20 or 25)", V);
     TG_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "graph_agg_fwd: stats must both be set");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TAMGCN_BF16) {
+        const int rc = graph_agg_fwd_mma(N, K, C, T, V, y, y_nstride, A, out, out_nstride, stat_sum, stat_sumsq, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     const dim3 grid = agg_grid(N, C);
     const size_t sm = sizeof(float) * K * V * ((V + 3) & ~3);
 #define AGG_FWD(T_, V_)                                                                                        \
@@ -195,6 +205,10 @@ extern "C" int tamgcn_graph_agg_bwd(int dtype, int N, int K, int C, int T, int V
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 grid = agg_grid(N, C);
     const Opnd go = make_opnd(dout);
+    if (dtype == TAMGCN_BF16) {
+        const int rc = graph_agg_bwd_mma(N, K, C, T, V, go, y, y_nstride, A, dy, dy_nstride, dA, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
     const size_t sm = sizeof(float) * K * V * ((V + 3) & ~3);
 #define AGG_DY(T_, V_) graph_agg_dy_kernel<T_, V_><<<grid, 256, sm, st>>>(N, K, C, T, go, A, (T_*)dy, dy_nstride)
     if (dtype == TAMGCN_F32) { if (V == 20) AGG_DY(float, 20); else AGG_DY(float, 25); }

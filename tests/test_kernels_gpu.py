@@ -383,25 +383,30 @@ def test_maxpool(dt, stride, T, V):
     assert rel(outs[0][0], outs[1][0]) < tol(dt) and rel(outs[0][1], outs[1][1]) < tol(dt)
 
 
-@pytest.mark.parametrize('dt,V,T', [(dt, V, T) for dt in DT for V, T in ((25, 30), (20, 9))])
-def test_graph_agg(dt, V, T):
+@pytest.mark.parametrize('dt,V,T,K,mode', [(dt, V, T, K, m) for dt in DT
+                                           for V, T, K, m in ((25, 30, 3, 'two'), (20, 9, 3, 'two'), (25, 75, 3, 'affine_relu'),
+                                                              (25, 300, 3, 'plain'), (20, 52, 2, 'two'), (25, 17, 1, 'two'),
+                                                              (25, 16, 3, 'wide'))])
+def test_graph_agg(dt, V, T, K, mode):
+    """75 / 17 rows of 25 joints: planes start at every 2-byte alignment; 'wide': operands are channel slices."""
     _dev()
     from tam_gcn_b200 import ops
-    N, K, C = 5, 3, 12
+    N, C = 5, 12
     g = gen(11)
-    y = rnd(g, N, K * C, T, V, dt=dt)
+    wide = mode == 'wide'
+    y = rnd(g, N, K * C + (7 if wide else 0), T, V, dt=dt)[:, :K * C]
     A = rnd(g, K, V, V, scale=0.3)
     outs = []
     for fn in (ops.graph_agg_fwd, E.graph_agg_fwd):
-        o = torch.zeros(N, C, T, V, device='cuda', dtype=dt)
+        o = torch.zeros(N, C + (3 if wide else 0), T, V, device='cuda', dtype=dt)[:, :C]
         st = torch.zeros(2, C, device='cuda', dtype=torch.float64)
         fn(y, A, o, stats=(st[0], st[1]))
         outs.append((o, st))
     assert rel(outs[0][0], outs[1][0]) < tol(dt) and rel(outs[0][1], outs[1][1]) < tol(dt)
-    go = make_operand(g, N, C, T, V, dt, 'two')
+    go = make_operand(g, N, C, T, V, dt, 'two' if wide else mode, wide=wide)
     outs = []
     for fn, conv in ((ops.graph_agg_bwd, real_opnd), (E.graph_agg_bwd, lambda o: o)):
-        dy = torch.zeros_like(y)
+        dy = torch.zeros(N, K * C + (7 if wide else 0), T, V, device='cuda', dtype=dt)[:, :K * C]
         dA = torch.zeros_like(A)
         fn(conv(go), y, A, dy, dA)
         outs.append((dy, dA))
