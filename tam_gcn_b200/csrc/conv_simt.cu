@@ -339,6 +339,10 @@ int conv_dgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const void* wpack, 
 int conv_wgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
 int conv_wgrad_tc2(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
 // warp-level MMA kernels for the small-channel temporal convolutions, tconv_mma.cu (kind: 0 forward, 1 data gradient)
+size_t conv_pack_t9_offset(int Cout, int Cin, int k, int dgrad);
+int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& in,
+                  const void* wpack9, const float* bias, void* out, long long ons, const Opnd* mask, double* s1, double* s2,
+                  int stat_c0, cudaStream_t st);
 int tconv_mma_fwd_dgrad(const tamgcn_conv_geom* g, int kind, const Opnd& in, const float* W, const float* bias, void* out,
                         long long ons, const Opnd* mask, double* s1, double* s2, int stat_c0, cudaStream_t st);
 int tconv_mma_wgrad(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* db, cudaStream_t st);
@@ -417,7 +421,11 @@ extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgc
     const Opnd xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        int rc = tconv_mma_fwd_dgrad(g, 0, xo, W, bias, y, y_nstride, nullptr, stat_sum, stat_sumsq, stat_c0, st);
+        int rc = tconv9_launch(0, p.N, p.Cin, p.Cout, p.T, p.V, p.k, p.s, p.d, p.p, xo,
+                               wpack ? (const unsigned char*)wpack + conv_pack_t9_offset(p.Cout, p.Cin, p.k, 0) : nullptr, bias, y,
+                               y_nstride, nullptr, stat_sum, stat_sumsq, stat_c0, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+        rc = tconv_mma_fwd_dgrad(g, 0, xo, W, bias, y, y_nstride, nullptr, stat_sum, stat_sumsq, stat_c0, st);
         if (rc != 0) return rc < 0 ? rc : 0;
         rc = conv_fwd_tc(g, xo, wpack, bias, y, y_nstride, stat_sum, stat_sumsq, stat_c0, st);
         if (rc != 0) return rc < 0 ? rc : 0;
@@ -456,7 +464,13 @@ extern "C" int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tam
     if (mask) mo = make_opnd(mask);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        int rc = (!addend && !bcast) ? tconv_mma_fwd_dgrad(g, 1, dyo, W, nullptr, dx, dx_nstride, mask ? &mo : nullptr, s1, s2, 0, st) : 0;
+        int rc = (!addend && !bcast)
+                     ? tconv9_launch(1, p.N, p.Cin, p.Cout, p.T, p.V, p.k, p.s, p.d, p.p, dyo,
+                                     wpack ? (const unsigned char*)wpack + conv_pack_t9_offset(p.Cout, p.Cin, p.k, 1) : nullptr,
+                                     nullptr, dx, dx_nstride, mask ? &mo : nullptr, s1, s2, 0, st)
+                     : 0;
+        if (rc != 0) return rc < 0 ? rc : 0;
+        rc = (!addend && !bcast) ? tconv_mma_fwd_dgrad(g, 1, dyo, W, nullptr, dx, dx_nstride, mask ? &mo : nullptr, s1, s2, 0, st) : 0;
         if (rc != 0) return rc < 0 ? rc : 0;
         rc = conv_dgrad_tc(g, dyo, wpack, dx, dx_nstride, addend, addend_nstride, bcast, bcast_scale,
                            mask ? &mo : nullptr, s1, s2, st);

@@ -19,6 +19,7 @@
 //               full-sector coalesced stores.
 // Persistent warp-specialised CTA, one per SM: warps 0-7 epilogue, warp 8 MMA issue, warps 9-16 producers.
 #include "tc_common.cuh"
+#include "tconv9_pack.cuh"
 #include <cstdlib>
 
 namespace tamgcn {
@@ -588,6 +589,8 @@ __device__ __forceinline__ void pack_w2_body(const float* __restrict__ W, int Co
             o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
             dst[((long long)ch * OCp + oc) * 8 + (piece ^ (oc & 7))] = o;
         }
+        // the tiles of the V-padded temporal-convolution kernel (tconv9.cu) follow in the same buffer
+        t9_pack_region(W, Cout, Cin, k, which, dst + units, t0, tstride);
     }
 }
 
@@ -621,9 +624,14 @@ static bool c2_disabled() {
 static int c2_num_sms() { return main_sms(); }
 static int oc_pad128(int OC) { return (OC + 127) & ~127; }
 
-size_t conv_pack_bytes(int Cout, int Cin, int k, int dgrad) {
+// offset of the tconv9 tiles inside a packed-weight buffer = size of the conv_tc2 tiles
+size_t conv_pack_t9_offset(int Cout, int Cin, int k, int dgrad) {
     const int OC = dgrad ? Cin : Cout, IC = dgrad ? Cout : Cin;
     return (size_t)((k * IC + 63) / 64) * (size_t)oc_pad128(OC) * 128;
+}
+size_t conv_pack_bytes(int Cout, int Cin, int k, int dgrad) {
+    const int OC = dgrad ? Cin : Cout, IC = dgrad ? Cout : Cin;
+    return conv_pack_t9_offset(Cout, Cin, k, dgrad) + t9_bytes(OC, IC, k);
 }
 
 int conv_pack_weights_batched(const long long* table, int njobs, cudaStream_t st) {

@@ -1,0 +1,399 @@
+// tconv9.cu — (k x 1) temporal convolution, k <= 9, stride 1, for V = 25 joints on tcgen05: forward and data gradient
+// of the ST-GCN temporal convolution (reference models/stgcn.py:76-82, nn.Conv2d(C, C, (9, 1), padding (4, 0))).
+//
+//   D[oc, (t, v)] = sum_{tap} sum_{ic} Wp[tap][oc][ic] * X[ic][(t + tap - pad, v)]
+//
+// The k taps read the SAME input rows shifted in time.  conv_tc2.cu flattens the taps into the GEMM K dimension and
+// fetches the activation once per tap, element by element because a 25-joint row is 50 bytes; here an input tile is
+// fetched ONCE and the taps are descriptor offsets:
+//   B operand (activations): a stage holds 16 input channels x (16 + k - 1) time steps; every (channel, time step) row
+//       is padded from 25 to 32 joints = 64 bytes, so a time step of 8 channels is one 512-byte SWIZZLE_64B atom of an
+//       MN-major operand ([channel half][time step][8 rows x 64 B]).  Tap j of a 16-step output tile is the same tile
+//       with the start address advanced by j atoms.  Rows are fetched as the aligned 16-byte words that hold them,
+//       realigned in registers (tc_realign16), run through the lazy operand f(a P + b Q + c) and stored with four
+//       16-byte shared-memory stores.  Time steps outside [0, T) are zero rows (the convolution's padding).
+//   A operand (weights): MN-major SWIZZLE_128B blocks of 128 output channels x 16 input channels per tap, pre-packed
+//       (tconv9_pack.cuh); the k blocks of a stage arrive with one bulk async copy.
+//   D: TMEM, 128 lanes (output channels) x 512 columns (16 time steps x 32 padded joints); 2 k MMAs (N = 256, K = 16)
+//       per stage.  The 7 padding columns of a time step are computed and dropped.
+//   epilogue: 8 warps, thread = channel: bias / ReLU mask, BatchNorm sums of the values as stored, bf16; two time steps
+//       (100 contiguous bytes per channel) are staged per warp and leave as 16-byte stores.
+// Persistent warp-specialised CTA, one per SM: warps 0-7 epilogue, warp 8 MMA issue, warps 9-16 loaders.
+#include "tc_common.cuh"
+#include "tconv9_pack.cuh"
+#include <cstdlib>
+
+namespace tamgcn {
+
+#define T9_V 25
+#define T9_TT 16
+#define T9_ROWS (T9_TT + T9_MAXK - 1)            // 24 time steps per stage
+#define T9_B_BYTES (2 * T9_ROWS * 512)           // [channel half][time step][8 x 64 B]
+#define T9_SMAX 4
+#define T9_EPI_W 8
+#define T9_LD_W 8
+#define T9_MMA_W T9_EPI_W
+#define T9_LD_W0 (T9_EPI_W + 1)
+#define T9_THREADS ((T9_EPI_W + 1 + T9_LD_W) * 32)
+#define T9_STG_ROW 128                           // staging pitch: 2 time steps x 50 B + up to 14 B of misalignment
+#define T9_STG_BYTES (T9_EPI_W * 32 * T9_STG_ROW)
+
+struct T9P {
+    int N, IC, OC, T, k, pad;
+    int n_mt, n_kc, n_tb, n_tiles;
+    int S, mode;
+    long long ons;
+    uint32_t a_bytes, stage_bytes, off_hdr, off_stg;
+};
+struct T9Epi {
+    const float* bias;
+    double* s1;
+    double* s2;
+    int stat_c0;
+    const bf16* maskp;
+    long long maskns;
+    const float* maska;
+    const float* maskc;
+    int has_mask;
+};
+struct T9Hdr {
+    uint64_t full[T9_SMAX], empty[T9_SMAX], tfull, tempty;
+    uint32_t tmem_base;
+    volatile uint32_t error;
+};
+
+__device__ __forceinline__ bool t9_wait(T9Hdr* hdr, uint64_t* bar, uint32_t parity) {
+    if (hdr->error) return false;
+    if (!mbar_wait(bar, parity)) { hdr->error = 1; return false; }
+    return true;
+}
+// MN-major SWIZZLE_128B (weights): LBO = distance between 64-channel halves, SBO = 1024 (8 K rows x 128 B)
+__device__ __forceinline__ uint64_t t9_desc_a(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// MN-major SWIZZLE_64B (activations): LBO = distance between time steps (512 B atoms), SBO = distance between the two
+// 8-channel halves
+__device__ __forceinline__ uint64_t t9_desc_b(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)((T9_ROWS * 512) >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+// One row of 25 bf16 at a 2-byte aligned address: the four 16-byte granules that hold it (50 + misalignment <= 64 bytes,
+// so exactly four, each containing bytes of the row), realigned to three chunks of 8 elements + the last element.
+__device__ __forceinline__ void t9_load_row(const bf16* rowp, uint4 (&c)[3], uint32_t& e24) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(rowp);
+    const uint32_t sft = (uint32_t)(a & 15);
+    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint4 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+    if (sft == 0) {
+        c[0] = w0; c[1] = w1; c[2] = w2;
+        e24 = w3.x & 0xffffu;
+    } else {
+        c[0] = tc_realign16(w0, w1, sft);
+        c[1] = tc_realign16(w1, w2, sft);
+        c[2] = tc_realign16(w2, w3, sft);
+        const uint32_t ws = sft >> 2;
+        const uint32_t w = ws == 0 ? w3.x : (ws == 1 ? w3.y : (ws == 2 ? w3.z : w3.w));
+        e24 = (sft & 2u) ? (w >> 16) : (w & 0xffffu);
+    }
+}
+__device__ __forceinline__ float t9_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float t9_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t t9_xf2(uint32_t p, uint32_t q, const OpCoef& cf, bool has_q, bool relu) {
+    float lo = fmaf(cf.a, t9_lo(p), cf.c), hi = fmaf(cf.a, t9_hi(p), cf.c);
+    if (has_q) { lo = fmaf(cf.b, t9_lo(q), lo); hi = fmaf(cf.b, t9_hi(q), hi); }
+    if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+    return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ uint4 t9_xf8(const uint4& p, const uint4& q, const OpCoef& cf, bool has_q, bool relu) {
+    return make_uint4(t9_xf2(p.x, q.x, cf, has_q, relu), t9_xf2(p.y, q.y, cf, has_q, relu), t9_xf2(p.z, q.z, cf, has_q, relu),
+                      t9_xf2(p.w, q.w, cf, has_q, relu));
+}
+
+// 25 bf16 given as 13 words (pairs, the last word's high half unused) -> shared memory at element offset E (any parity)
+__device__ __forceinline__ void t9_stage_row(unsigned char* row, int E, const uint32_t (&W)[13]) {
+    if ((E & 1) == 0) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(row) + (E >> 1);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) d[i] = W[i];
+        reinterpret_cast<unsigned short*>(row)[E + 24] = (unsigned short)(W[12] & 0xffffu);
+    } else {
+        reinterpret_cast<unsigned short*>(row)[E] = (unsigned short)(W[0] & 0xffffu);
+        uint32_t* d = reinterpret_cast<uint32_t*>(row) + ((E + 1) >> 1);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) d[i] = __funnelshift_r(W[i], W[i + 1], 16);
+    }
+}
+
+__global__ void __launch_bounds__(T9_THREADS, 1)
+tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __restrict__ out, T9Epi ep) {
+    extern __shared__ unsigned char t9_smem[];
+    const uint32_t raw = smem_u32(t9_smem);
+    const uint32_t s0 = (raw + 1023u) & ~1023u;
+    unsigned char* sbase = t9_smem + (s0 - raw);
+    T9Hdr* hdr = reinterpret_cast<T9Hdr*>(sbase + p.off_hdr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int V = T9_V;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.S; ++s) { mbar_init(&hdr->full[s], T9_LD_W); mbar_init(&hdr->empty[s], 1); }
+        mbar_init(&hdr->tfull, 1);
+        mbar_init(&hdr->tempty, T9_EPI_W);
+        hdr->error = 0;
+        fence_mbar_init();
+    }
+    if (warp == T9_MMA_W) tmem_alloc(&hdr->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = hdr->tmem_base;
+    const int tile0 = blockIdx.x, tstep = gridDim.x;
+
+    if (warp < T9_EPI_W) {
+        // =============================== epilogue ===============================
+        const int q = warp & 3, hh = warp >> 2;                  // TMEM lane quarter, half of the 16 time steps
+        unsigned char* stg = sbase + p.off_stg + (size_t)warp * 32 * T9_STG_ROW;
+        unsigned char* myrow = stg + (size_t)lane * T9_STG_ROW;
+        float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
+        int it = 0;
+        for (int tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
+            const int mt = tile % p.n_mt, rest = tile / p.n_mt, tb = rest % p.n_tb, n = rest / p.n_tb;
+            const int t0 = tb * T9_TT;
+            if (!t9_wait(hdr, &hdr->tfull, (uint32_t)(it & 1))) break;
+            tc_fence_after();
+            const int chw = mt * 128 + q * 32, ch = chw + lane;
+            const bool chv = ch < p.OC;
+            if (chw < p.OC) {
+                const float bias_ = (p.mode == 0 && ep.bias && chv) ? __ldg(ep.bias + ch) : 0.f;
+                float ma_ = 1.f, mc_ = 0.f;
+                if (ep.has_mask && chv) {
+                    if (ep.maska) ma_ = __ldg(ep.maska + ch);
+                    if (ep.maskc) mc_ = __ldg(ep.maskc + ch);
+                }
+                float s1acc = 0.f, s2acc = 0.f;
+#pragma unroll 1
+                for (int pp = 0; pp < 4; ++pp) {
+                    const int tau0 = hh * 8 + 2 * pp;
+                    if (t0 + tau0 >= p.T) break;
+                    const int nst = min(2, p.T - (t0 + tau0));
+                    const long long e_base = ((long long)ch * p.T + t0 + tau0) * V;        // inside a sample
+                    const int mis = (int)(reinterpret_cast<uintptr_t>(out + (long long)n * p.ons + e_base) & 15);
+#pragma unroll 1
+                    for (int s = 0; s < nst; ++s) {
+                        float acc[32];
+                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tau0 + s) * 32), acc);
+                        uint32_t W[13];
+                        if (p.mode == 0) {
+#pragma unroll
+                            for (int i = 0; i < 13; ++i) {
+                                const uint32_t w = pack_bf16(acc[2 * i] + bias_, (2 * i + 1 < V) ? acc[2 * i + 1] + bias_ : 0.f);
+                                const float lo = t9_lo(w), hi = t9_hi(w);
+                                s1acc += lo + hi;
+                                s2acc = fmaf(lo, lo, fmaf(hi, hi, s2acc));
+                                W[i] = w;
+                            }
+                        } else if (ep.has_mask) {
+                            uint4 mk[3];
+                            uint32_t m24 = 0u;
+                            if (chv) t9_load_row(ep.maskp + (long long)n * ep.maskns + e_base + (long long)s * V, mk, m24);
+                            else { mk[0] = mk[1] = mk[2] = make_uint4(0u, 0u, 0u, 0u); }
+                            const uint32_t mw[13] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w,
+                                                     mk[2].x, mk[2].y, mk[2].z, mk[2].w, m24};
+#pragma unroll
+                            for (int i = 0; i < 13; ++i) {
+                                const float m0 = t9_lo(mw[i]), m1 = t9_hi(mw[i]);
+                                float v0 = acc[2 * i], v1 = (2 * i + 1 < V) ? acc[2 * i + 1] : 0.f;
+                                if (!(fmaf(ma_, m0, mc_) > 0.f)) v0 = 0.f;
+                                if (!(fmaf(ma_, m1, mc_) > 0.f)) v1 = 0.f;
+                                const uint32_t w = pack_bf16(v0, v1);
+                                const float lo = t9_lo(w), hi = (2 * i + 1 < V) ? t9_hi(w) : 0.f;
+                                s1acc += lo + hi;
+                                s2acc = fmaf(lo, m0, fmaf(hi, m1, s2acc));
+                                W[i] = w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 13; ++i) W[i] = pack_bf16(acc[2 * i], (2 * i + 1 < V) ? acc[2 * i + 1] : 0.f);
+                        }
+                        t9_stage_row(myrow, (mis >> 1) + s * V, W);
+                    }
+                    __syncwarp();
+                    // copy-out: 4 rows x 8 chunks per iteration; whole 16-byte chunks as vector stores
+                    const int nbytes = nst * V * 2;
+#pragma unroll 1
+                    for (int r4 = 0; r4 < 8; ++r4) {
+                        const int row = r4 * 4 + (lane >> 3), o = (lane & 7) * 16;
+                        const int chr = chw + row;
+                        if (chr < p.OC) {
+                            unsigned char* dst = reinterpret_cast<unsigned char*>(out + (long long)n * p.ons + ((long long)chr * p.T + t0 + tau0) * V);
+                            const int mr = (int)(reinterpret_cast<uintptr_t>(dst) & 15);
+                            const unsigned char* src = stg + (size_t)row * T9_STG_ROW;
+                            if (o >= mr && o + 16 <= mr + nbytes) {
+                                *reinterpret_cast<uint4*>(dst - mr + o) = *reinterpret_cast<const uint4*>(src + o);
+                            } else if (o + 16 > mr && o < mr + nbytes) {
+#pragma unroll
+                                for (int b = 0; b < 16; b += 2)
+                                    if (o + b >= mr && o + b < mr + nbytes)
+                                        *reinterpret_cast<unsigned short*>(dst - mr + o + b) = *reinterpret_cast<const unsigned short*>(src + o + b);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (chv) { st1[mt & 1] += s1acc; st2[mt & 1] += s2acc; }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->tempty);
+        }
+        if (ep.s1 && !hdr->error) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const int ch = m * 128 + q * 32 + lane;
+                if (m < p.n_mt && ch < p.OC && ch >= ep.stat_c0 && (st1[m] != 0.f || st2[m] != 0.f)) {
+                    atomicAdd(ep.s1 + (ch - ep.stat_c0), (double)st1[m]);
+                    atomicAdd(ep.s2 + (ch - ep.stat_c0), (double)st2[m]);
+                }
+            }
+        }
+    } else if (warp == T9_MMA_W) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, 256) | (1u << 15) | (1u << 16);     // A and B MN-major
+            int stg = 0, ph = 0, it = 0;
+            bool ok = true;
+            for (int tile = tile0; tile < p.n_tiles && ok; tile += tstep, ++it) {
+                if (!t9_wait(hdr, &hdr->tempty, (uint32_t)((it & 1) ^ 1))) break;
+                tc_fence_after();
+                for (int kc = 0; kc < p.n_kc; ++kc) {
+                    if (!mbar_wait_spin(&hdr->full[stg], (uint32_t)ph)) { hdr->error = 1; ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t sa = s0 + (uint32_t)stg * p.stage_bytes, sb = sa + p.a_bytes;
+                    for (int j = 0; j < p.k; ++j) {
+                        const uint64_t ad = t9_desc_a(sa + (uint32_t)j * T9_BLK_BYTES);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            umma_bf16(tmem + (uint32_t)(h * 256), ad, t9_desc_b(sb + (uint32_t)(j + 8 * h) * 512u), idesc,
+                                      (kc > 0 || j > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&hdr->empty[stg]);
+                    if (++stg == p.S) { stg = 0; ph ^= 1; }
+                }
+                if (ok) umma_commit(&hdr->tfull);
+            }
+        }
+    } else {
+        // =============================== loaders ===============================
+        const int ltid = threadIdx.x - T9_LD_W0 * 32;
+        const bool has_q = x.q != nullptr, relu = x.relu != 0;
+        int stg = 0, ph = 0;
+        bool ok = true;
+        for (int tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
+            const int mt = tile % p.n_mt, rest = tile / p.n_mt, tb = rest % p.n_tb, n = rest / p.n_tb;
+            const int t0 = tb * T9_TT;
+            const int nrows = min(T9_TT, p.T - t0) + p.k - 1;
+            const bf16* xp = (const bf16*)x.p + (long long)n * x.pns;
+            const bf16* xq = has_q ? (const bf16*)x.q + (long long)n * x.qns : nullptr;
+            for (int kc = 0; kc < p.n_kc; ++kc) {
+                if (!t9_wait(hdr, &hdr->empty[stg], (uint32_t)(ph ^ 1))) { ok = false; break; }
+                unsigned char* sa = sbase + (size_t)stg * p.stage_bytes;
+                if (ltid == 0) {
+                    mbar_expect_tx(&hdr->full[stg], p.a_bytes);
+                    bulk_g2s(s0 + (uint32_t)stg * p.stage_bytes, wpack + ((size_t)(mt * p.n_kc + kc) * p.k) * T9_BLK_BYTES, p.a_bytes,
+                             &hdr->full[stg]);
+                }
+                const uint32_t sb = s0 + (uint32_t)stg * p.stage_bytes + p.a_bytes;
+                (void)sa;
+                for (int idx = ltid; idx < 16 * nrows; idx += T9_LD_W * 32) {
+                    const int cl = idx / nrows, s = idx - cl * nrows;
+                    const int t = t0 - p.pad + s, ci = kc * 16 + cl;
+                    uint4 c[4];
+                    c[0] = c[1] = c[2] = c[3] = make_uint4(0u, 0u, 0u, 0u);
+                    if (t >= 0 && t < p.T) {
+                        const long long e = ((long long)ci * p.T + t) * V;
+                        uint4 pr[3], qr[3];
+                        uint32_t p24, q24 = 0u;
+                        t9_load_row(xp + e, pr, p24);
+                        if (has_q) t9_load_row(xq + e, qr, q24);
+                        else { qr[0] = qr[1] = qr[2] = make_uint4(0u, 0u, 0u, 0u); }
+                        if (x.a || x.c || has_q || relu) {
+                            const OpCoef cf = opnd_coef(x, ci);
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) c[i] = t9_xf8(pr[i], qr[i], cf, has_q, relu);
+                            c[3].x = t9_xf2(p24, q24, cf, has_q, relu) & 0xffffu;
+                        } else {
+                            c[0] = pr[0]; c[1] = pr[1]; c[2] = pr[2];
+                            c[3].x = p24;
+                        }
+                    }
+                    const uint32_t r = (uint32_t)cl & 7u, sw = (r >> 1) & 3u;
+                    const uint32_t rowa = sb + ((uint32_t)cl >> 3) * (T9_ROWS * 512u) + (uint32_t)s * 512u + r * 64u;
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i) st_shared_v4(rowa + ((i ^ sw) << 4), c[i].x, c[i].y, c[i].z, c[i].w);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hdr->full[stg]);
+                if (++stg == p.S) { stg = 0; ph ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == T9_MMA_W) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+static bool t9_disabled() {
+    static const bool off = [] { const char* e = getenv("TAMGCN_DISABLE_T9"); return e && e[0] == '1'; }();
+    return off;
+}
+
+// geometry covered by the kernel (shared by the dispatchers and tamgcn_conv_needs_pack)
+bool tconv9_covers(int Cin, int Cout, int k, int stride, int dil, int pad, int V, int dgrad) {
+    if (t9_disabled()) return false;
+    const int OC = dgrad ? Cin : Cout, IC = dgrad ? Cout : Cin;
+    return V == T9_V && stride == 1 && dil == 1 && 2 * pad == k - 1 && t9_eligible(OC, IC, k) && OC <= 256 && OC >= 64 && IC >= 64;
+}
+
+// mode 0: forward (in = x, out = y), mode 1: data gradient (in = dY, out = dX).  wpack9 = the tconv9 region of the
+// packed-weight buffer of that direction.  returns 1 if launched, 0 if not covered, < 0 on error
+int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& in,
+                  const void* wpack9, const float* bias, void* out, long long ons, const Opnd* mask, double* s1, double* s2,
+                  int stat_c0, cudaStream_t st) {
+    if (!wpack9 || !tconv9_covers(Cin, Cout, k, stride, dil, pad, V, mode)) return 0;
+    T9P p = {};
+    p.N = N; p.IC = mode ? Cout : Cin; p.OC = mode ? Cin : Cout; p.T = T; p.k = k; p.pad = pad;
+    p.n_mt = (p.OC + 127) / 128; p.n_kc = p.IC / 16; p.n_tb = (T + T9_TT - 1) / T9_TT;
+    const long long tiles = (long long)N * p.n_tb * p.n_mt;
+    if (tiles > 0x7fffffffLL) return 0;
+    p.n_tiles = (int)tiles;
+    p.mode = mode; p.ons = ons;
+    p.a_bytes = (uint32_t)k * T9_BLK_BYTES;
+    p.stage_bytes = (p.a_bytes + T9_B_BYTES + 1023u) & ~1023u;
+    const uint32_t budget = 227u * 1024u - 1024u;
+    const uint32_t szH = (sizeof(T9Hdr) + 15u) & ~15u;
+    int S = (int)((budget - szH - T9_STG_BYTES) / p.stage_bytes);
+    if (S > T9_SMAX) S = T9_SMAX;
+    if (S < 2) return 0;
+    p.S = S;
+    p.off_stg = (uint32_t)S * p.stage_bytes;
+    p.off_hdr = p.off_stg + T9_STG_BYTES;
+    const size_t sm = (size_t)p.off_hdr + szH + 1024;
+    T9Epi ep = {};
+    ep.bias = bias; ep.s1 = s1; ep.s2 = s2; ep.stat_c0 = stat_c0;
+    if (mask) { ep.has_mask = 1; ep.maskp = (const bf16*)mask->p; ep.maskns = mask->pns; ep.maska = mask->a; ep.maskc = mask->c; }
+    int grid = main_sms();
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    static SmemLimit lim;
+    ensure_smem(tconv9_kernel, lim, sm);
+    tconv9_kernel<<<grid, T9_THREADS, sm, st>>>(p, in, (const unsigned char*)wpack9, (bf16*)out, ep);
+    count_launch();
+    const int rc = check_launch(mode ? "conv_dgrad(tconv9)" : "conv_fwd(tconv9)");
+    return rc < 0 ? rc : 1;
+}
+
+}  // namespace tamgcn

@@ -530,7 +530,11 @@ int tconv_mma_wgrad(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, fl
 
 }  // namespace tamgcn
 
+namespace tamgcn { bool tconv9_covers(int Cin, int Cout, int k, int stride, int dil, int pad, int V, int dgrad); }
+
 extern "C" int tamgcn_conv_needs_pack(int Cin, int Cout, int k, int stride, int V, int dgrad) {
+    // the V-padded tcgen05 kernel (tconv9.cu) takes "same" temporal convolutions of V = 25 first and reads packed tiles
+    if ((k & 1) && tamgcn::tconv9_covers(Cin, Cout, k, stride, 1, (k - 1) / 2, V, dgrad)) return 1;
     // mirrors tm_setup: the MMA kernels read the fp32 weights directly, the tcgen05 kernels need the packed tiles
     if (tamgcn::tm_disabled()) return 1;
     const bool small = (Cin == Cout) && (Cin == 16 || Cin == 32 || Cin == 64) && k >= 2 && k <= TM_MAXK && V <= 32;
