@@ -18,9 +18,13 @@
 //       per stage.  The 7 padding columns of a time step are computed and dropped.
 //   epilogue: 8 warps, thread = channel: bias / ReLU mask, BatchNorm sums of the values as stored, bf16; two time steps
 //       (100 contiguous bytes per channel) are staged per warp and leave as 16-byte stores.
-// Persistent warp-specialised CTA, one per SM: warps 0-7 epilogue, warp 8 MMA issue, warps 9-16 loaders.
+// Persistent warp-specialised CTA, one per SM: warps 0-7 epilogue (one accumulator: the epilogue of a tile and the MMAs
+// of the next never overlap, so lane 0 of warp 0 is also the MMA issuer), warps 8-19 loaders (a loader thread
+// owns the same (channel, time step) slot of every stage and requests the row of the next stage before it transforms and
+// stores the current one, so a stage's global-memory latency hides behind the previous stage).
 #include "tc_common.cuh"
 #include "tconv9_pack.cuh"
+#include <cstdio>
 #include <cstdlib>
 
 namespace tamgcn {
@@ -31,17 +35,17 @@ namespace tamgcn {
 #define T9_B_BYTES (2 * T9_ROWS * 512)           // [channel half][time step][8 x 64 B]
 #define T9_SMAX 4
 #define T9_EPI_W 8
-#define T9_LD_W 8
-#define T9_MMA_W T9_EPI_W
-#define T9_LD_W0 (T9_EPI_W + 1)
-#define T9_THREADS ((T9_EPI_W + 1 + T9_LD_W) * 32)
-#define T9_STG_ROW 128                           // staging pitch: 2 time steps x 50 B + up to 14 B of misalignment
+#define T9_LD_W 12                             // 384 loader threads: one (channel, time step) row of a stage each
+#define T9_LD_W0 T9_EPI_W
+#define T9_THREADS ((T9_EPI_W + T9_LD_W) * 32)    // 640: 20 warps leave 96 registers per thread
+#define T9_STG_ROW 144                           // staging pitch: 2 time steps x 50 B + up to 14 B of misalignment; 144 = 36
+                                                 // words keeps a warp's 16-byte row reads conflict-free
 #define T9_STG_BYTES (T9_EPI_W * 32 * T9_STG_ROW)
 
 struct T9P {
     int N, IC, OC, T, k, pad;
     int n_mt, n_kc, n_tb, n_tiles;
-    int S, mode;
+    int S, mode, dbg;
     long long ons;
     uint32_t a_bytes, stage_bytes, off_hdr, off_stg;
 };
@@ -126,6 +130,7 @@ __device__ __forceinline__ void t9_stage_row(unsigned char* row, int E, const ui
     }
 }
 
+template <bool HASQ>
 __global__ void __launch_bounds__(T9_THREADS, 1)
 tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __restrict__ out, T9Epi ep) {
     extern __shared__ unsigned char t9_smem[];
@@ -143,7 +148,7 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
         hdr->error = 0;
         fence_mbar_init();
     }
-    if (warp == T9_MMA_W) tmem_alloc(&hdr->tmem_base, 512);
+    if (warp == 0) tmem_alloc(&hdr->tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -156,11 +161,46 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
         unsigned char* stg = sbase + p.off_stg + (size_t)warp * 32 * T9_STG_ROW;
         unsigned char* myrow = stg + (size_t)lane * T9_STG_ROW;
         float st1[2] = {0.f, 0.f}, st2[2] = {0.f, 0.f};
-        int it = 0;
+        const uint32_t idesc = umma_idesc_bf16(128, 256) | (1u << 15) | (1u << 16);     // A and B MN-major
+        int it = 0, mstg = 0, mph = 0;
+        long long tw_full = 0, tw_tempty = 0, t_epi = 0, t_mma = 0;
+        const long long t_begin = clock64();
         for (int tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
             const int mt = tile % p.n_mt, rest = tile / p.n_mt, tb = rest % p.n_tb, n = rest / p.n_tb;
             const int t0 = tb * T9_TT;
+            if (warp == 0) {
+                // ---- MMA issue for this tile (one thread) ----
+                const long long tq0 = clock64();
+                if (lane == 0 && t9_wait(hdr, &hdr->tempty, (uint32_t)((it & 1) ^ 1))) {
+                    tw_tempty += clock64() - tq0;
+                    const long long tm0 = clock64();
+                    tc_fence_after();
+                    bool ok = true;
+                    for (int kc = 0; kc < p.n_kc; ++kc) {
+                        const long long tf0 = clock64();
+                        if (!mbar_wait_spin(&hdr->full[mstg], (uint32_t)mph)) { hdr->error = 1; ok = false; break; }
+                        tw_full += clock64() - tf0;
+                        tc_fence_after();
+                        const uint32_t sa = s0 + (uint32_t)mstg * p.stage_bytes, sb = sa + p.a_bytes;
+                        for (int j = 0; j < p.k; ++j) {
+                            const uint64_t ad = t9_desc_a(sa + (uint32_t)j * T9_BLK_BYTES);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                umma_bf16(tmem + (uint32_t)(h * 256), ad, t9_desc_b(sb + (uint32_t)(j + 8 * h) * 512u), idesc,
+                                          (kc > 0 || j > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&hdr->empty[mstg]);
+                        if (++mstg == p.S) { mstg = 0; mph ^= 1; }
+                    }
+                    if (ok) umma_commit(&hdr->tfull);
+                    t_mma += clock64() - tm0;
+                }
+                __syncwarp();
+            }
+            const long long tt0 = clock64();
             if (!t9_wait(hdr, &hdr->tfull, (uint32_t)(it & 1))) break;
+            const long long te0 = clock64();
+            if (warp == 0) t_mma += te0 - tt0;
             tc_fence_after();
             const int chw = mt * 128 + q * 32, ch = chw + lane;
             const bool chv = ch < p.OC;
@@ -218,35 +258,34 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
                         }
                         t9_stage_row(myrow, (mis >> 1) + s * V, W);
                     }
-                    __syncwarp();
-                    // copy-out: 4 rows x 8 chunks per iteration; whole 16-byte chunks as vector stores
-                    const int nbytes = nst * V * 2;
-#pragma unroll 1
-                    for (int r4 = 0; r4 < 8; ++r4) {
-                        const int row = r4 * 4 + (lane >> 3), o = (lane & 7) * 16;
-                        const int chr = chw + row;
-                        if (chr < p.OC) {
-                            unsigned char* dst = reinterpret_cast<unsigned char*>(out + (long long)n * p.ons + ((long long)chr * p.T + t0 + tau0) * V);
-                            const int mr = (int)(reinterpret_cast<uintptr_t>(dst) & 15);
-                            const unsigned char* src = stg + (size_t)row * T9_STG_ROW;
-                            if (o >= mr && o + 16 <= mr + nbytes) {
-                                *reinterpret_cast<uint4*>(dst - mr + o) = *reinterpret_cast<const uint4*>(src + o);
-                            } else if (o + 16 > mr && o < mr + nbytes) {
+                    // copy-out (thread-private row): whole 16-byte chunks as vector stores, the ragged head / tail by element
+                    if (chv) {
+                        const int nbytes = nst * V * 2;
+                        unsigned char* dst = reinterpret_cast<unsigned char*>(out + (long long)n * p.ons + e_base) - mis;
 #pragma unroll
-                                for (int b = 0; b < 16; b += 2)
-                                    if (o + b >= mr && o + b < mr + nbytes)
-                                        *reinterpret_cast<unsigned short*>(dst - mr + o + b) = *reinterpret_cast<const unsigned short*>(src + o + b);
+                        for (int c8 = 0; c8 < 8; ++c8) {
+                            const int o = c8 * 16;
+                            if (o >= mis && o + 16 <= mis + nbytes) {
+                                *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(myrow + o);
+                            } else if (o + 16 > mis && o < mis + nbytes) {
+#pragma unroll
+                                for (int b2 = 0; b2 < 16; b2 += 2)
+                                    if (o + b2 >= mis && o + b2 < mis + nbytes)
+                                        *reinterpret_cast<unsigned short*>(dst + o + b2) = *reinterpret_cast<const unsigned short*>(myrow + o + b2);
                             }
                         }
                     }
-                    __syncwarp();
                 }
                 if (chv) { st1[mt & 1] += s1acc; st2[mt & 1] += s2acc; }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&hdr->tempty);
+            t_epi += clock64() - te0;
         }
+        if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5))
+            printf("tconv9 block 0 warp %d: tiles %d total %lld | wait tempty %lld  issue+wait full %lld (blocked on full %lld)  epilogue %lld\n",
+                   warp, it, clock64() - t_begin, tw_tempty, t_mma, tw_full, t_epi);
         if (ep.s1 && !hdr->error) {
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -257,91 +296,117 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
                 }
             }
         }
-    } else if (warp == T9_MMA_W) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, 256) | (1u << 15) | (1u << 16);     // A and B MN-major
-            int stg = 0, ph = 0, it = 0;
-            bool ok = true;
-            for (int tile = tile0; tile < p.n_tiles && ok; tile += tstep, ++it) {
-                if (!t9_wait(hdr, &hdr->tempty, (uint32_t)((it & 1) ^ 1))) break;
-                tc_fence_after();
-                for (int kc = 0; kc < p.n_kc; ++kc) {
-                    if (!mbar_wait_spin(&hdr->full[stg], (uint32_t)ph)) { hdr->error = 1; ok = false; break; }
-                    tc_fence_after();
-                    const uint32_t sa = s0 + (uint32_t)stg * p.stage_bytes, sb = sa + p.a_bytes;
-                    for (int j = 0; j < p.k; ++j) {
-                        const uint64_t ad = t9_desc_a(sa + (uint32_t)j * T9_BLK_BYTES);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            umma_bf16(tmem + (uint32_t)(h * 256), ad, t9_desc_b(sb + (uint32_t)(j + 8 * h) * 512u), idesc,
-                                      (kc > 0 || j > 0) ? 1u : 0u);
-                    }
-                    umma_commit(&hdr->empty[stg]);
-                    if (++stg == p.S) { stg = 0; ph ^= 1; }
-                }
-                if (ok) umma_commit(&hdr->tfull);
-            }
-        }
     } else {
         // =============================== loaders ===============================
         const int ltid = threadIdx.x - T9_LD_W0 * 32;
-        const bool has_q = x.q != nullptr, relu = x.relu != 0;
+        constexpr bool has_q = HASQ;
+        const bool relu = x.relu != 0, lazy = x.a || x.c || has_q || relu;
+        // this thread's slot: row s of the stage, channel cl (channel fastest: the 8 lanes of a store phase then write the 8
+        // rows of one 512-byte atom, which the swizzle spreads over all banks)
+        const int s = ltid >> 4, cl = ltid & 15;
+        const uint32_t r = (uint32_t)cl & 7u, sw = (r >> 1) & 3u;
+        const uint32_t slot = p.a_bytes + ((uint32_t)cl >> 3) * (T9_ROWS * 512u) + (uint32_t)s * 512u + r * 64u;
+        // raw granules of a row in flight
+        uint4 pw[4], qw[HASQ ? 4 : 1], npw[4], nqw[HASQ ? 4 : 1];
+        uint32_t sftp = 0, sftq = 0, nsftp = 0, nsftq = 0;
+        bool live = false, nlive = false;
+        int ci_cur = 0, ci_nxt = 0;
+        OpCoef cf = {1.f, 0.f, 0.f}, ncf = {1.f, 0.f, 0.f};
+        // (tile, kc) of the row to request next
+        int l_tile = tile0, l_kc = 0;
+        auto request = [&]() {
+            nlive = false;
+            if (l_tile < p.n_tiles) {
+                const int rest = l_tile / p.n_mt, tb = rest % p.n_tb, n = rest / p.n_tb;
+                const int t0 = tb * T9_TT;
+                const int nrows = min(T9_TT, p.T - t0) + p.k - 1;
+                const int t = t0 - p.pad + s;
+                ci_nxt = l_kc * 16 + cl;
+                if (s < nrows && t >= 0 && t < p.T) {
+                    nlive = true;
+                    if (lazy) ncf = opnd_coef(x, ci_nxt);
+                    const long long e = ((long long)ci_nxt * p.T + t) * V;
+                    {
+                        const uintptr_t a = reinterpret_cast<uintptr_t>((const bf16*)x.p + (long long)n * x.pns + e);
+                        nsftp = (uint32_t)(a & 15);
+                        const uint4* g = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                        npw[0] = __ldg(g); npw[1] = __ldg(g + 1); npw[2] = __ldg(g + 2); npw[3] = __ldg(g + 3);
+                    }
+                    if (has_q) {
+                        const uintptr_t a = reinterpret_cast<uintptr_t>((const bf16*)x.q + (long long)n * x.qns + e);
+                        nsftq = (uint32_t)(a & 15);
+                        const uint4* g = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                        nqw[0] = __ldg(g); nqw[1] = __ldg(g + 1); nqw[2] = __ldg(g + 2); nqw[3] = __ldg(g + 3);
+                    }
+                }
+                if (++l_kc == p.n_kc) { l_kc = 0; l_tile += tstep; }
+            }
+        };
+        auto split = [&](const uint4* w, uint32_t sft, uint4 (&c)[3], uint32_t& e24) {
+            if (sft == 0) {
+                c[0] = w[0]; c[1] = w[1]; c[2] = w[2];
+                e24 = w[3].x & 0xffffu;
+            } else {
+                c[0] = tc_realign16(w[0], w[1], sft);
+                c[1] = tc_realign16(w[1], w[2], sft);
+                c[2] = tc_realign16(w[2], w[3], sft);
+                const uint32_t ws = sft >> 2;
+                const uint32_t ww = ws == 0 ? w[3].x : (ws == 1 ? w[3].y : (ws == 2 ? w[3].z : w[3].w));
+                e24 = (sft & 2u) ? (ww >> 16) : (ww & 0xffffu);
+            }
+        };
         int stg = 0, ph = 0;
-        bool ok = true;
+        bool ok = ltid < 16 * T9_ROWS;
+        long long tw_empty = 0;
+        const long long tl_begin = clock64();
+        request();
         for (int tile = tile0; tile < p.n_tiles && ok; tile += tstep) {
-            const int mt = tile % p.n_mt, rest = tile / p.n_mt, tb = rest % p.n_tb, n = rest / p.n_tb;
-            const int t0 = tb * T9_TT;
-            const int nrows = min(T9_TT, p.T - t0) + p.k - 1;
-            const bf16* xp = (const bf16*)x.p + (long long)n * x.pns;
-            const bf16* xq = has_q ? (const bf16*)x.q + (long long)n * x.qns : nullptr;
+            const int mt = tile % p.n_mt;
             for (int kc = 0; kc < p.n_kc; ++kc) {
+                // the requested row becomes the current one; the row of the next stage is requested right away
+                live = nlive; ci_cur = ci_nxt; sftp = nsftp; sftq = nsftq; cf = ncf;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { pw[i] = npw[i]; if (HASQ) qw[i] = nqw[i]; }
+                request();
+                const long long tw0 = clock64();
                 if (!t9_wait(hdr, &hdr->empty[stg], (uint32_t)(ph ^ 1))) { ok = false; break; }
-                unsigned char* sa = sbase + (size_t)stg * p.stage_bytes;
+                tw_empty += clock64() - tw0;
+                const uint32_t sst = s0 + (uint32_t)stg * p.stage_bytes;
                 if (ltid == 0) {
                     mbar_expect_tx(&hdr->full[stg], p.a_bytes);
-                    bulk_g2s(s0 + (uint32_t)stg * p.stage_bytes, wpack + ((size_t)(mt * p.n_kc + kc) * p.k) * T9_BLK_BYTES, p.a_bytes,
-                             &hdr->full[stg]);
+                    bulk_g2s(sst, wpack + ((size_t)(mt * p.n_kc + kc) * p.k) * T9_BLK_BYTES, p.a_bytes, &hdr->full[stg]);
                 }
-                const uint32_t sb = s0 + (uint32_t)stg * p.stage_bytes + p.a_bytes;
-                (void)sa;
-                for (int idx = ltid; idx < 16 * nrows; idx += T9_LD_W * 32) {
-                    const int cl = idx / nrows, s = idx - cl * nrows;
-                    const int t = t0 - p.pad + s, ci = kc * 16 + cl;
-                    uint4 c[4];
-                    c[0] = c[1] = c[2] = c[3] = make_uint4(0u, 0u, 0u, 0u);
-                    if (t >= 0 && t < p.T) {
-                        const long long e = ((long long)ci * p.T + t) * V;
-                        uint4 pr[3], qr[3];
-                        uint32_t p24, q24 = 0u;
-                        t9_load_row(xp + e, pr, p24);
-                        if (has_q) t9_load_row(xq + e, qr, q24);
+                uint4 c[4];
+                c[0] = c[1] = c[2] = c[3] = make_uint4(0u, 0u, 0u, 0u);
+                if (live) {
+                    uint4 pr[3], qr[3];
+                    uint32_t p24, q24 = 0u;
+                    split(pw, sftp, pr, p24);
+                    if (lazy) {
+                        if (has_q) split(qw, sftq, qr, q24);
                         else { qr[0] = qr[1] = qr[2] = make_uint4(0u, 0u, 0u, 0u); }
-                        if (x.a || x.c || has_q || relu) {
-                            const OpCoef cf = opnd_coef(x, ci);
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) c[i] = t9_xf8(pr[i], qr[i], cf, has_q, relu);
-                            c[3].x = t9_xf2(p24, q24, cf, has_q, relu) & 0xffffu;
-                        } else {
-                            c[0] = pr[0]; c[1] = pr[1]; c[2] = pr[2];
-                            c[3].x = p24;
-                        }
+                        for (int i = 0; i < 3; ++i) c[i] = t9_xf8(pr[i], qr[i], cf, has_q, relu);
+                        c[3].x = t9_xf2(p24, q24, cf, has_q, relu) & 0xffffu;
+                    } else {
+                        c[0] = pr[0]; c[1] = pr[1]; c[2] = pr[2];
+                        c[3].x = p24;
                     }
-                    const uint32_t r = (uint32_t)cl & 7u, sw = (r >> 1) & 3u;
-                    const uint32_t rowa = sb + ((uint32_t)cl >> 3) * (T9_ROWS * 512u) + (uint32_t)s * 512u + r * 64u;
-#pragma unroll
-                    for (uint32_t i = 0; i < 4; ++i) st_shared_v4(rowa + ((i ^ sw) << 4), c[i].x, c[i].y, c[i].z, c[i].w);
                 }
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i) st_shared_v4(sst + slot + ((i ^ sw) << 4), c[i].x, c[i].y, c[i].z, c[i].w);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hdr->full[stg]);
                 if (++stg == p.S) { stg = 0; ph ^= 1; }
             }
         }
+        if ((p.dbg & 8) && blockIdx.x == 0 && (ltid == 0 || ltid == 200))
+            printf("tconv9 block 0 loader %d: total %lld | blocked on empty %lld\n", ltid, clock64() - tl_begin, tw_empty);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == T9_MMA_W) {
+    if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
@@ -372,6 +437,7 @@ int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int V, int k, int s
     if (tiles > 0x7fffffffLL) return 0;
     p.n_tiles = (int)tiles;
     p.mode = mode; p.ons = ons;
+    { const char* e = getenv("TAMGCN_T9_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.a_bytes = (uint32_t)k * T9_BLK_BYTES;
     p.stage_bytes = (p.a_bytes + T9_B_BYTES + 1023u) & ~1023u;
     const uint32_t budget = 227u * 1024u - 1024u;
@@ -388,9 +454,15 @@ int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int V, int k, int s
     if (mask) { ep.has_mask = 1; ep.maskp = (const bf16*)mask->p; ep.maskns = mask->pns; ep.maska = mask->a; ep.maskc = mask->c; }
     int grid = main_sms();
     if (grid > p.n_tiles) grid = p.n_tiles;
-    static SmemLimit lim;
-    ensure_smem(tconv9_kernel, lim, sm);
-    tconv9_kernel<<<grid, T9_THREADS, sm, st>>>(p, in, (const unsigned char*)wpack9, (bf16*)out, ep);
+    if (in.q) {
+        static SmemLimit lim;
+        ensure_smem(tconv9_kernel<true>, lim, sm);
+        tconv9_kernel<true><<<grid, T9_THREADS, sm, st>>>(p, in, (const unsigned char*)wpack9, (bf16*)out, ep);
+    } else {
+        static SmemLimit lim;
+        ensure_smem(tconv9_kernel<false>, lim, sm);
+        tconv9_kernel<false><<<grid, T9_THREADS, sm, st>>>(p, in, (const unsigned char*)wpack9, (bf16*)out, ep);
+    }
     count_launch();
     const int rc = check_launch(mode ? "conv_dgrad(tconv9)" : "conv_fwd(tconv9)");
     return rc < 0 ? rc : 1;
