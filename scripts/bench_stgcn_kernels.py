@@ -67,3 +67,23 @@ for C, T in SHAPES:
         fl = 2.0 * N * T * V * C * C * k
         print('conv C=%3d T=%3d  fwd %7.1f us %5.1f TF/s | dgrad %7.1f us %5.1f TF/s | wgrad %7.1f us %5.1f TF/s' %
               (C, T, tf, fl / tf / 1e6, td, fl / td / 1e6, tw, fl / tw / 1e6))
+
+if what in ('all', 'gcn'):
+    # the 1x1 graph convolution Cin -> K*Cout of every layer (models/stgcn.py:47-53)
+    for Cin, Cout, T in ((3, 64, 300), (64, 64, 300), (64, 128, 300), (128, 128, 150), (128, 256, 150), (256, 256, 75)):
+        KC = K * Cout
+        x = rnd(N, Cin, T, V)
+        W = torch.randn(KC, Cin, device=dev, generator=g) * Cin ** -0.5
+        b = torch.zeros(KC, device=dev)
+        yo = torch.empty(N, KC, T, V, device=dev, dtype=torch.bfloat16)
+        wf, wd = ops.conv_pack_weights(W, KC, Cin, 1, 1, V)
+        gy = rnd(N, KC, T, V)
+        dx = torch.empty_like(x)
+        dW = torch.zeros_like(W)
+        db = torch.zeros(KC, device=dev)
+        tf = timeit(lambda: ops.conv_fwd(x, W, b, yo, 1, 1, 1, 0, wpack=wf))
+        td = timeit(lambda: ops.conv_dgrad(gy, W, dx, 1, 1, 1, 0, wpack=wd))
+        tw = timeit(lambda: ops.conv_wgrad(gy, x, dW, db, 1, 1, 1, 0))
+        by = 2.0 * (x.numel() + yo.numel())
+        print('gcn  %3d->%3d T=%3d  fwd %7.1f us %5.0f GB/s | dgrad %7.1f us %5.0f GB/s | wgrad %7.1f us %5.0f GB/s' %
+              (Cin, KC, T, tf, by / tf / 1e3, td, by / td / 1e3, tw, by / tw / 1e3))

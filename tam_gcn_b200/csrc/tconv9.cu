@@ -66,7 +66,8 @@ struct T9Hdr {
     volatile uint32_t error;
 };
 
-__device__ __forceinline__ bool t9_wait(T9Hdr* hdr, uint64_t* bar, uint32_t parity) {
+template <typename H>
+__device__ __forceinline__ bool t9_wait(H* hdr, uint64_t* bar, uint32_t parity) {
     if (hdr->error) return false;
     if (!mbar_wait(bar, parity)) { hdr->error = 1; return false; }
     return true;
@@ -412,6 +413,278 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
     }
 }
 
+// =====================================================================================================================
+// weight gradient:  dW[co][ci][j] += sum_{n,t,v} dY[n,co,t,v] X[n,ci,t+j-pad,v],   db[co] += sum dY
+//
+// One CTA = one work item (128 output channels, <= 32 input channels, one sample, a segment of time steps); the k taps
+// are k accumulators of 32 TMEM columns.  Both operands are K-major SWIZZLE_128B with the (time, padded joint) positions
+// as K: a 128-byte row holds two time steps of one channel, so tap j of time step t is the X tile read at K offset
+// (t + j) * 32 elements — a start-address offset of 64 bytes per time step inside the swizzled rows, as the per-MMA
+// K advance of every K-major kernel here.  Per stage: 8 time steps of dY (4 K blocks x 128 rows) and the 16 time steps
+// of X they touch (8 K blocks x 32 rows); 2 x 8 x k MMAs (M = 128, N = 32, K = 16).  The loaders are the forward
+// kernel's (aligned granules, register realignment, lazy operand), with the row of the next slot requested before the
+// current one is transformed.  Drain: TMEM -> the idle stage memory as [co][ci*k + j] rows (the memory order of dW for a
+// 32-channel tile) -> coalesced red.global.add.v4.f32.
+// =====================================================================================================================
+#define W9_TS 8                                   // time steps of dY per stage
+#define W9_A_BYTES (4 * 128 * 128)                // 4 K blocks x 128 rows x 128 B
+#define W9_B_BYTES (8 * 32 * 128)                 // 8 K blocks x 32 rows x 128 B
+#define W9_STAGE_BYTES (W9_A_BYTES + W9_B_BYTES)  // 96 KB
+#define W9_S 2
+#define W9_DRAIN_PITCH (32 * T9_MAXK * 4 + 16)    // staging row of the drain: 288 floats + 16 B (bank spread)
+
+struct W9P {
+    int N, Cin, Cout, T, k, pad;
+    int n_cot, n_cit, n_seg, seg_stages;          // item = ((n * n_seg + seg) * n_cot + cot) * n_cit + cit
+    uint32_t off_hdr;
+};
+struct W9Hdr {
+    uint64_t full[W9_S], empty[W9_S], done;
+    uint32_t tmem_base;
+    volatile uint32_t error;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <bool HASQ>
+__global__ void __launch_bounds__(T9_THREADS, 1)
+tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __restrict__ db) {
+    extern __shared__ unsigned char t9_smem[];
+    const uint32_t raw = smem_u32(t9_smem);
+    const uint32_t s0 = (raw + 1023u) & ~1023u;
+    unsigned char* sbase = t9_smem + (s0 - raw);
+    W9Hdr* hdr = reinterpret_cast<W9Hdr*>(sbase + p.off_hdr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int V = T9_V;
+
+    int item = blockIdx.x;
+    const int cit = item % p.n_cit; item /= p.n_cit;
+    const int cot = item % p.n_cot; item /= p.n_cot;
+    const int seg = item % p.n_seg;
+    const int n = item / p.n_seg;
+    const int NB = min(32, p.Cin - cit * 32);                     // input channels of this tile (16 or 32)
+    const int stage0 = seg * p.seg_stages;
+    const int n_st = min(p.seg_stages, (p.T + W9_TS - 1) / W9_TS - stage0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < W9_S; ++s) { mbar_init(&hdr->full[s], T9_LD_W); mbar_init(&hdr->empty[s], 1); }
+        mbar_init(&hdr->done, 1);
+        hdr->error = 0;
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(&hdr->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = hdr->tmem_base;
+
+    if (warp < T9_EPI_W) {
+        if (warp == 0 && lane == 0) {
+            // ---- MMA issue ----
+            const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)NB);
+            int stg = 0, ph = 0;
+            bool ok = true;
+            for (int st = 0; st < n_st && ok; ++st) {
+                if (!mbar_wait_spin(&hdr->full[stg], (uint32_t)ph)) { hdr->error = 1; ok = false; break; }
+                tc_fence_after();
+                const uint32_t sa = s0 + (uint32_t)stg * W9_STAGE_BYTES, sb = sa + W9_A_BYTES;
+                for (int tau = 0; tau < W9_TS; ++tau) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t ad = umma_desc_sw128(sa + (uint32_t)(tau >> 1) * 16384u + (uint32_t)((tau & 1) * 64 + h * 32));
+                        for (int j = 0; j < p.k; ++j) {
+                            const int sx = tau + j;                       // X time-step slot of the stage
+                            const uint64_t bd = umma_desc_sw128(sb + (uint32_t)(sx >> 1) * 4096u + (uint32_t)((sx & 1) * 64 + h * 32));
+                            umma_bf16(tmem + (uint32_t)(j * 32), ad, bd, idesc, (st > 0 || tau > 0 || h > 0) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(&hdr->empty[stg]);
+                if (++stg == W9_S) { stg = 0; ph ^= 1; }
+            }
+            if (ok) umma_commit(&hdr->done);
+        }
+        __syncwarp();
+        // ---- drain ----
+        if (t9_wait(hdr, &hdr->done, 0u)) {
+            tc_fence_after();
+            const int q = warp & 3, hh = warp >> 2;                  // lane quarter; the two warps of a quarter split the taps
+            const int co = q * 32 + lane;
+            unsigned char* rowp = sbase + (size_t)co * W9_DRAIN_PITCH;
+            const int rowlen = NB * p.k;                             // floats of a dW row segment of this tile
+            for (int j = hh; j < p.k; j += 2) {
+                float acc[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), acc);
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c < NB) reinterpret_cast<float*>(rowp)[c * p.k + j] = acc[c];
+            }
+            // both warps of a quarter must have written their taps before rows are read back
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
+            const int nv4 = rowlen / 4;                              // NB * k is a multiple of 4 (NB = 16 / 32)
+            for (int r = hh; r < 32; r += 2) {
+                const int cor = cot * 128 + q * 32 + r;
+                if (cor >= p.Cout) break;
+                const unsigned char* src = sbase + (size_t)(q * 32 + r) * W9_DRAIN_PITCH;
+                float* dst = dW + ((long long)cor * p.Cin + cit * 32) * p.k;
+                for (int i = lane; i < nv4; i += 32) red_add_v4(dst + 4 * i, *reinterpret_cast<const float4*>(src + 16 * i));
+            }
+        }
+    } else {
+        // =============================== loaders ===============================
+        const int ltid = threadIdx.x - T9_LD_W0 * 32;
+        constexpr bool has_q = HASQ;
+        const bool lazy_a = dy.a || dy.c || has_q || dy.relu, relu_a = dy.relu != 0;
+        const bool lazy_b = x.a || x.c || x.relu, relu_b = x.relu != 0;
+        // slots of this thread in a stage: A rows (co = ltid & 127, steps (ltid >> 7) + 3 i), B rows (idx = ltid + 384 i)
+        const int a_co = ltid & 127, a_s0 = ltid >> 7;
+        const int cha = cot * 128 + a_co;
+        const bool a_chv = cha < p.Cout;
+        const OpCoef cfa = a_chv && lazy_a ? opnd_coef(dy, cha) : OpCoef{1.f, 0.f, 0.f};
+        float dbsum = 0.f;
+        uint4 pw[4], qw[HASQ ? 4 : 1], npw[4], nqw[HASQ ? 4 : 1];
+        uint32_t sftp = 0, sftq = 0, nsftp = 0, nsftq = 0;
+        int kind = 0, nkind = 0;              // 0 skip, 1 zero row, 2 A row, 3 B row
+        uint32_t dsto = 0, ndsto = 0;         // byte offset of the row (chunk 0, unswizzled) inside the stage
+        uint32_t rsw = 0, nrsw = 0;           // row & 7 (swizzle key)
+        OpCoef cfb = {1.f, 0.f, 0.f}, ncfb = {1.f, 0.f, 0.f};
+        int l_st = 0, l_q = 0;                // (stage, slot) to request next
+        auto request = [&]() {
+            nkind = 0;
+            if (l_st >= n_st) return;
+            const int t_stage = (stage0 + l_st) * W9_TS;
+            if (l_q < 3) {
+                const int step = a_s0 + 3 * l_q;
+                if (step < W9_TS) {
+                    const int t = t_stage + step;
+                    ndsto = (uint32_t)(step >> 1) * 16384u + (uint32_t)a_co * 128u + (uint32_t)(step & 1) * 64u;
+                    nrsw = (uint32_t)a_co & 7u;
+                    nkind = 1;
+                    if (a_chv && t < p.T) {
+                        nkind = 2;
+                        const long long e = ((long long)cha * p.T + t) * V;
+                        {
+                            const uintptr_t a = reinterpret_cast<uintptr_t>((const bf16*)dy.p + (long long)n * dy.pns + e);
+                            nsftp = (uint32_t)(a & 15);
+                            const uint4* g = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                            npw[0] = __ldg(g); npw[1] = __ldg(g + 1); npw[2] = __ldg(g + 2); npw[3] = __ldg(g + 3);
+                        }
+                        if (has_q) {
+                            const uintptr_t a = reinterpret_cast<uintptr_t>((const bf16*)dy.q + (long long)n * dy.qns + e);
+                            nsftq = (uint32_t)(a & 15);
+                            const uint4* g = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                            nqw[0] = __ldg(g); nqw[1] = __ldg(g + 1); nqw[2] = __ldg(g + 2); nqw[3] = __ldg(g + 3);
+                        }
+                    }
+                }
+            } else {
+                const int idx = ltid + 384 * (l_q - 3);
+                if (idx < 512) {
+                    const int cl = idx & 31, sx = idx >> 5;
+                    if (cl < NB) {
+                        const int t = t_stage - p.pad + sx, ci = cit * 32 + cl;
+                        ndsto = W9_A_BYTES + (uint32_t)(sx >> 1) * 4096u + (uint32_t)cl * 128u + (uint32_t)(sx & 1) * 64u;
+                        nrsw = (uint32_t)cl & 7u;
+                        nkind = 1;
+                        if (t >= 0 && t < p.T) {
+                            nkind = 3;
+                            if (lazy_b) ncfb = opnd_coef(x, ci);
+                            const uintptr_t a = reinterpret_cast<uintptr_t>((const bf16*)x.p + (long long)n * x.pns + ((long long)ci * p.T + t) * V);
+                            nsftp = (uint32_t)(a & 15);
+                            const uint4* g = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+                            npw[0] = __ldg(g); npw[1] = __ldg(g + 1); npw[2] = __ldg(g + 2); npw[3] = __ldg(g + 3);
+                        }
+                    }
+                }
+            }
+        };
+        auto advance = [&]() { if (++l_q == 5) { l_q = 0; ++l_st; } };
+        auto split = [&](const uint4* w, uint32_t sft, uint4 (&c)[3], uint32_t& e24) {
+            if (sft == 0) {
+                c[0] = w[0]; c[1] = w[1]; c[2] = w[2];
+                e24 = w[3].x & 0xffffu;
+            } else {
+                c[0] = tc_realign16(w[0], w[1], sft);
+                c[1] = tc_realign16(w[1], w[2], sft);
+                c[2] = tc_realign16(w[2], w[3], sft);
+                const uint32_t ws = sft >> 2;
+                const uint32_t ww = ws == 0 ? w[3].x : (ws == 1 ? w[3].y : (ws == 2 ? w[3].z : w[3].w));
+                e24 = (sft & 2u) ? (ww >> 16) : (ww & 0xffffu);
+            }
+        };
+        int stg = 0, ph = 0;
+        bool ok = true;
+        request();
+        advance();
+        for (int st = 0; st < n_st && ok; ++st) {
+            for (int qslot = 0; qslot < 5; ++qslot) {
+                kind = nkind; dsto = ndsto; rsw = nrsw; sftp = nsftp; sftq = nsftq; cfb = ncfb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { pw[i] = npw[i]; if (HASQ) qw[i] = nqw[i]; }
+                request();
+                advance();
+                if (qslot == 0 && !t9_wait(hdr, &hdr->empty[stg], (uint32_t)(ph ^ 1))) { ok = false; break; }
+                if (kind == 0) continue;
+                uint4 c[4];
+                c[0] = c[1] = c[2] = c[3] = make_uint4(0u, 0u, 0u, 0u);
+                if (kind == 2) {
+                    uint4 pr[3], qr[3];
+                    uint32_t p24, q24 = 0u;
+                    split(pw, sftp, pr, p24);
+                    if (lazy_a) {
+                        if (has_q) split(qw, sftq, qr, q24);
+                        else { qr[0] = qr[1] = qr[2] = make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) c[i] = t9_xf8(pr[i], qr[i], cfa, has_q, relu_a);
+                        c[3].x = t9_xf2(p24, q24, cfa, has_q, relu_a) & 0xffffu;
+                    } else {
+                        c[0] = pr[0]; c[1] = pr[1]; c[2] = pr[2];
+                        c[3].x = p24;
+                    }
+                    if (db && cit == 0) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            dbsum += (t9_lo(c[i].x) + t9_hi(c[i].x)) + (t9_lo(c[i].y) + t9_hi(c[i].y)) + (t9_lo(c[i].z) + t9_hi(c[i].z)) +
+                                     (t9_lo(c[i].w) + t9_hi(c[i].w));
+                        dbsum += t9_lo(c[3].x);
+                    }
+                } else if (kind == 3) {
+                    uint4 pr[3];
+                    uint32_t p24;
+                    split(pw, sftp, pr, p24);
+                    if (lazy_b) {
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) c[i] = t9_xf8(pr[i], z, cfb, false, relu_b);
+                        c[3].x = t9_xf2(p24, 0u, cfb, false, relu_b) & 0xffffu;
+                    } else {
+                        c[0] = pr[0]; c[1] = pr[1]; c[2] = pr[2];
+                        c[3].x = p24;
+                    }
+                }
+                const uint32_t rowa = s0 + (uint32_t)stg * W9_STAGE_BYTES + (dsto & ~127u);
+                const uint32_t c0 = (dsto & 64u) >> 4;                   // first 16-byte chunk of the time step inside the row
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i) st_shared_v4(rowa + (((c0 + i) ^ rsw) << 4), c[i].x, c[i].y, c[i].z, c[i].w);
+            }
+            if (!ok) break;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hdr->full[stg]);
+            if (++stg == W9_S) { stg = 0; ph ^= 1; }
+        }
+        if (db && cit == 0 && a_chv && dbsum != 0.f) atomicAdd(db + cha, dbsum);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 static bool t9_disabled() {
     static const bool off = [] { const char* e = getenv("TAMGCN_DISABLE_T9"); return e && e[0] == '1'; }();
     return off;
@@ -465,6 +738,45 @@ int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int V, int k, int s
     }
     count_launch();
     const int rc = check_launch(mode ? "conv_dgrad(tconv9)" : "conv_fwd(tconv9)");
+    return rc < 0 ? rc : 1;
+}
+
+// returns 1 if launched, 0 if not covered, < 0 on error
+int tconv9_wgrad_launch(int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& dy, const Opnd& x,
+                        float* dW, float* db, cudaStream_t st) {
+    if (t9_disabled()) return 0;
+    static const bool off = [] { const char* e = getenv("TAMGCN_DISABLE_T9W"); return e && e[0] == '1'; }();
+    if (off) return 0;
+    if (!(V == T9_V && stride == 1 && dil == 1 && 2 * pad == k - 1 && k >= 2 && k <= T9_MAXK && Cin % 16 == 0 && Cin >= 32 && Cout >= 32))
+        return 0;
+    if (x.q) return 0;                                     // the X operand is a one-tensor lazy operand
+    if ((reinterpret_cast<uintptr_t>(dW) & 15) != 0) return 0;
+    W9P p = {};
+    p.N = N; p.Cin = Cin; p.Cout = Cout; p.T = T; p.k = k; p.pad = pad;
+    p.n_cot = (Cout + 127) / 128; p.n_cit = (Cin + 31) / 32;
+    const int stages = (T + W9_TS - 1) / W9_TS;
+    // segments per sample: enough items for ~2.5 waves of CTAs, at least 4 stages per item
+    const long long base_items = (long long)N * p.n_cot * p.n_cit;
+    int n_seg = (int)((5LL * wgrad_sms() / 2 + base_items - 1) / base_items);
+    if (n_seg > (stages + 3) / 4) n_seg = (stages + 3) / 4;
+    if (n_seg < 1) n_seg = 1;
+    p.seg_stages = (stages + n_seg - 1) / n_seg;
+    p.n_seg = (stages + p.seg_stages - 1) / p.seg_stages;
+    const long long items = base_items * p.n_seg;
+    if (items > 0x7fffffffLL) return 0;
+    p.off_hdr = W9_S * W9_STAGE_BYTES;
+    const size_t sm = (size_t)p.off_hdr + ((sizeof(W9Hdr) + 15) & ~15u) + 1024;
+    if (dy.q) {
+        static SmemLimit lim;
+        ensure_smem(tconv9_wgrad_kernel<true>, lim, sm);
+        tconv9_wgrad_kernel<true><<<(int)items, T9_THREADS, sm, st>>>(p, dy, x, dW, db);
+    } else {
+        static SmemLimit lim;
+        ensure_smem(tconv9_wgrad_kernel<false>, lim, sm);
+        tconv9_wgrad_kernel<false><<<(int)items, T9_THREADS, sm, st>>>(p, dy, x, dW, db);
+    }
+    count_launch();
+    const int rc = check_launch("conv_wgrad(tconv9)");
     return rc < 0 ? rc : 1;
 }
 
