@@ -340,7 +340,7 @@ int conv_wgrad_tc(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, floa
 int conv_wgrad_tc2(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* dbias, cudaStream_t st);
 // warp-level MMA kernels for the small-channel temporal convolutions, tconv_mma.cu (kind: 0 forward, 1 data gradient)
 size_t conv_pack_t9_offset(int Cout, int Cin, int k, int dgrad);
-int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& in,
+int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int To, int V, int k, int stride, int dil, int pad, const Opnd& in,
                   const void* wpack9, const float* bias, void* out, long long ons, const Opnd* mask, double* s1, double* s2,
                   int stat_c0, cudaStream_t st);
 int tconv9_wgrad_launch(int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& dy, const Opnd& x,
@@ -423,7 +423,7 @@ extern "C" int tamgcn_conv_fwd(const tamgcn_conv_geom* g, int dtype, const tamgc
     const Opnd xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        int rc = tconv9_launch(0, p.N, p.Cin, p.Cout, p.T, p.V, p.k, p.s, p.d, p.p, xo,
+        int rc = tconv9_launch(0, p.N, p.Cin, p.Cout, p.T, p.To, p.V, p.k, p.s, p.d, p.p, xo,
                                wpack ? (const unsigned char*)wpack + conv_pack_t9_offset(p.Cout, p.Cin, p.k, 0) : nullptr, bias, y,
                                y_nstride, nullptr, stat_sum, stat_sumsq, stat_c0, st);
         if (rc != 0) return rc < 0 ? rc : 0;
@@ -467,7 +467,7 @@ extern "C" int tamgcn_conv_dgrad(const tamgcn_conv_geom* g, int dtype, const tam
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
         int rc = (!addend && !bcast)
-                     ? tconv9_launch(1, p.N, p.Cin, p.Cout, p.T, p.V, p.k, p.s, p.d, p.p, dyo,
+                     ? tconv9_launch(1, p.N, p.Cin, p.Cout, p.T, p.To, p.V, p.k, p.s, p.d, p.p, dyo,
                                      wpack ? (const unsigned char*)wpack + conv_pack_t9_offset(p.Cout, p.Cin, p.k, 1) : nullptr,
                                      nullptr, dx, dx_nstride, mask ? &mo : nullptr, s1, s2, 0, st)
                      : 0;

@@ -43,7 +43,10 @@ namespace tamgcn {
 #define T9_STG_BYTES (T9_EPI_W * 32 * T9_STG_ROW)
 
 struct T9P {
-    int N, IC, OC, T, k, pad;
+    int N, IC, OC, T, k, pad;     // T = time steps of the OUTPUT tensor
+    int Tin;                      // time steps of the input tensor
+    int var;                      // 0: stride 1;  1: forward, stride 2;  2: data gradient of a stride-2 convolution
+    int tt;                       // output time steps per tile (16, variant 1: 8)
     int n_mt, n_kc, n_tb, n_tiles;
     int S, mode, dbg;
     long long ons;
@@ -79,8 +82,8 @@ __device__ __forceinline__ uint64_t t9_desc_a(uint32_t saddr) {
 }
 // MN-major SWIZZLE_64B (activations): LBO = distance between time steps (512 B atoms), SBO = distance between the two
 // 8-channel halves
-__device__ __forceinline__ uint64_t t9_desc_b(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(512 >> 4) << 16) | ((uint64_t)((T9_ROWS * 512) >> 4) << 32) |
+__device__ __forceinline__ uint64_t t9_desc_b(uint32_t saddr, uint32_t lbo = 512u) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)((T9_ROWS * 512) >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 
@@ -168,7 +171,7 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
         const long long t_begin = clock64();
         for (int tile = tile0; tile < p.n_tiles; tile += tstep, ++it) {
             const int mt = tile % p.n_mt, rest = tile / p.n_mt, tb = rest % p.n_tb, n = rest / p.n_tb;
-            const int t0 = tb * T9_TT;
+            const int t0 = tb * p.tt;
             if (warp == 0) {
                 // ---- MMA issue for this tile (one thread) ----
                 const long long tq0 = clock64();
@@ -183,12 +186,26 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
                         tw_full += clock64() - tf0;
                         tc_fence_after();
                         const uint32_t sa = s0 + (uint32_t)mstg * p.stage_bytes, sb = sa + p.a_bytes;
-                        for (int j = 0; j < p.k; ++j) {
-                            const uint64_t ad = t9_desc_a(sa + (uint32_t)j * T9_BLK_BYTES);
+                        if (p.var == 0) {
+                            for (int j = 0; j < p.k; ++j) {
+                                const uint64_t ad = t9_desc_a(sa + (uint32_t)j * T9_BLK_BYTES);
 #pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                                umma_bf16(tmem + (uint32_t)(h * 256), ad, t9_desc_b(sb + (uint32_t)(j + 8 * h) * 512u), idesc,
+                                for (int h = 0; h < 2; ++h)
+                                    umma_bf16(tmem + (uint32_t)(h * 256), ad, t9_desc_b(sb + (uint32_t)(j + 8 * h) * 512u), idesc,
+                                              (kc > 0 || j > 0) ? 1u : 0u);
+                            }
+                        } else if (p.var == 1) {
+                            // stride 2: output step tau reads row 2 tau + j — every second atom (LBO = 2 atoms), 8 steps per tile
+                            for (int j = 0; j < p.k; ++j)
+                                umma_bf16(tmem, t9_desc_a(sa + (uint32_t)j * T9_BLK_BYTES), t9_desc_b(sb + (uint32_t)j * 512u, 1024u), idesc,
                                           (kc > 0 || j > 0) ? 1u : 0u);
+                        } else {
+                            // gradient of a stride-2 convolution: output steps 2 u + e (e = 0, 1) use the taps j = e + 2 m on the
+                            // rows u + e - 2 + m of dY; phase e accumulates in columns e * 256 (8 values of u per tile)
+                            for (int e = 0; e < 2; ++e)
+                                for (int m = 0; e + 2 * m < p.k; ++m)
+                                    umma_bf16(tmem + (uint32_t)(e * 256), t9_desc_a(sa + (uint32_t)(e + 2 * m) * T9_BLK_BYTES),
+                                              t9_desc_b(sb + (uint32_t)(e + m) * 512u), idesc, (kc > 0 || m > 0) ? 1u : 0u);
                         }
                         umma_commit(&hdr->empty[mstg]);
                         if (++mstg == p.S) { mstg = 0; mph ^= 1; }
@@ -213,9 +230,10 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
                     if (ep.maskc) mc_ = __ldg(ep.maskc + ch);
                 }
                 float s1acc = 0.f, s2acc = 0.f;
+                const int half_steps = p.tt >> 1;
 #pragma unroll 1
-                for (int pp = 0; pp < 4; ++pp) {
-                    const int tau0 = hh * 8 + 2 * pp;
+                for (int pp = 0; 2 * pp < half_steps; ++pp) {
+                    const int tau0 = hh * half_steps + 2 * pp;
                     if (t0 + tau0 >= p.T) break;
                     const int nst = min(2, p.T - (t0 + tau0));
                     const long long e_base = ((long long)ch * p.T + t0 + tau0) * V;        // inside a sample
@@ -223,7 +241,9 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
 #pragma unroll 1
                     for (int s = 0; s < nst; ++s) {
                         float acc[32];
-                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((tau0 + s) * 32), acc);
+                        const int sg = tau0 + s;
+                        const int col = (p.var == 2) ? ((sg & 1) * 256 + (sg >> 1) * 32) : sg * 32;
+                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
                         uint32_t W[13];
                         if (p.mode == 0) {
 #pragma unroll
@@ -319,14 +339,17 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
             nlive = false;
             if (l_tile < p.n_tiles) {
                 const int rest = l_tile / p.n_mt, tb = rest % p.n_tb, n = rest / p.n_tb;
-                const int t0 = tb * T9_TT;
-                const int nrows = min(T9_TT, p.T - t0) + p.k - 1;
-                const int t = t0 - p.pad + s;
+                const int t0 = tb * p.tt;
+                const int nout = min(p.tt, p.T - t0);
+                int nrows, t;
+                if (p.var == 0) { nrows = nout + p.k - 1; t = t0 - p.pad + s; }
+                else if (p.var == 1) { nrows = 2 * (nout - 1) + p.k; t = 2 * t0 - p.pad + s; }
+                else { nrows = 12; t = (t0 >> 1) - 2 + s; }
                 ci_nxt = l_kc * 16 + cl;
-                if (s < nrows && t >= 0 && t < p.T) {
+                if (s < nrows && t >= 0 && t < p.Tin) {
                     nlive = true;
                     if (lazy) ncf = opnd_coef(x, ci_nxt);
-                    const long long e = ((long long)ci_nxt * p.T + t) * V;
+                    const long long e = ((long long)ci_nxt * p.Tin + t) * V;
                     {
                         const uintptr_t a = reinterpret_cast<uintptr_t>((const bf16*)x.p + (long long)n * x.pns + e);
                         nsftp = (uint32_t)(a & 15);
@@ -694,18 +717,23 @@ static bool t9_disabled() {
 bool tconv9_covers(int Cin, int Cout, int k, int stride, int dil, int pad, int V, int dgrad) {
     if (t9_disabled()) return false;
     const int OC = dgrad ? Cin : Cout, IC = dgrad ? Cout : Cin;
-    return V == T9_V && stride == 1 && dil == 1 && 2 * pad == k - 1 && t9_eligible(OC, IC, k) && OC <= 256 && OC >= 64 && IC >= 64;
+    const bool geom = (stride == 1 && 2 * pad == k - 1) || (stride == 2 && k == 9 && pad == 4);
+    return V == T9_V && dil == 1 && geom && t9_eligible(OC, IC, k) && OC <= 256 && OC >= 64 && IC >= 64;
 }
 
 // mode 0: forward (in = x, out = y), mode 1: data gradient (in = dY, out = dX).  wpack9 = the tconv9 region of the
 // packed-weight buffer of that direction.  returns 1 if launched, 0 if not covered, < 0 on error
-int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& in,
+int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int To, int V, int k, int stride, int dil, int pad, const Opnd& in,
                   const void* wpack9, const float* bias, void* out, long long ons, const Opnd* mask, double* s1, double* s2,
                   int stat_c0, cudaStream_t st) {
     if (!wpack9 || !tconv9_covers(Cin, Cout, k, stride, dil, pad, V, mode)) return 0;
     T9P p = {};
-    p.N = N; p.IC = mode ? Cout : Cin; p.OC = mode ? Cin : Cout; p.T = T; p.k = k; p.pad = pad;
-    p.n_mt = (p.OC + 127) / 128; p.n_kc = p.IC / 16; p.n_tb = (T + T9_TT - 1) / T9_TT;
+    // T = input length of the convolution, To = its output length; the data gradient reads To steps and writes T
+    p.N = N; p.IC = mode ? Cout : Cin; p.OC = mode ? Cin : Cout; p.k = k; p.pad = pad;
+    p.T = mode ? T : To; p.Tin = mode ? To : T;
+    p.var = stride == 1 ? 0 : (mode ? 2 : 1);
+    p.tt = p.var == 1 ? 8 : T9_TT;
+    p.n_mt = (p.OC + 127) / 128; p.n_kc = p.IC / 16; p.n_tb = (p.T + p.tt - 1) / p.tt;
     const long long tiles = (long long)N * p.n_tb * p.n_mt;
     if (tiles > 0x7fffffffLL) return 0;
     p.n_tiles = (int)tiles;

@@ -72,7 +72,9 @@ CONV_GEOMS = [  # (Cin, Cout, T, k, s, d)
     # the MS-TCN branch shapes served by the warp-MMA kernels (tconv_mma.cu)
     (16, 16, 52, 5, 1, 1), (32, 32, 26, 5, 2, 2), (64, 64, 13, 5, 1, 2), (32, 32, 9, 3, 1, 1), (16, 16, 7, 5, 2, 1),
     # the ST-GCN temporal convolutions served (at V = 25) by the V-padded tcgen05 kernel (tconv9.cu)
-    (64, 64, 40, 9, 1, 1), (128, 64, 35, 9, 1, 1), (64, 128, 75, 5, 1, 1), (256, 256, 19, 9, 1, 1), (64, 64, 300, 9, 1, 1)]
+    (64, 64, 40, 9, 1, 1), (128, 64, 35, 9, 1, 1), (64, 128, 75, 5, 1, 1), (256, 256, 19, 9, 1, 1), (64, 64, 300, 9, 1, 1),
+    # ... and the stride-2 layers (l5, l8)
+    (64, 64, 40, 9, 2, 1), (128, 128, 75, 9, 2, 1), (64, 128, 31, 9, 2, 1)]
 
 
 def _pad(k, d):
