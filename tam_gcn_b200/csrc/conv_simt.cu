@@ -343,8 +343,8 @@ size_t conv_pack_t9_offset(int Cout, int Cin, int k, int dgrad);
 int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int To, int V, int k, int stride, int dil, int pad, const Opnd& in,
                   const void* wpack9, const float* bias, void* out, long long ons, const Opnd* mask, double* s1, double* s2,
                   int stat_c0, cudaStream_t st);
-int tconv9_wgrad_launch(int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& dy, const Opnd& x,
-                        float* dW, float* db, cudaStream_t st);
+int tconv9_wgrad_launch(int N, int Cin, int Cout, int T, int To, int V, int k, int stride, int dil, int pad, const Opnd& dy,
+                        const Opnd& x, float* dW, float* db, cudaStream_t st);
 int tconv_mma_fwd_dgrad(const tamgcn_conv_geom* g, int kind, const Opnd& in, const float* W, const float* bias, void* out,
                         long long ons, const Opnd* mask, double* s1, double* s2, int stat_c0, cudaStream_t st);
 int tconv_mma_wgrad(const tamgcn_conv_geom* g, const Opnd& dy, const Opnd& x, float* dW, float* db, cudaStream_t st);
@@ -508,7 +508,7 @@ extern "C" int tamgcn_conv_wgrad(const tamgcn_conv_geom* g, int dtype, const tam
     const Opnd dyo = make_opnd(dy), xo = make_opnd(x);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TAMGCN_BF16) {
-        int rc = tconv9_wgrad_launch(p.N, p.Cin, p.Cout, p.T, p.V, p.k, p.s, p.d, p.p, dyo, xo, dW, dbias, st);   // tconv9.cu
+        int rc = tconv9_wgrad_launch(p.N, p.Cin, p.Cout, p.T, p.To, p.V, p.k, p.s, p.d, p.p, dyo, xo, dW, dbias, st);   // tconv9.cu
         if (rc != 0) return rc < 0 ? rc : 0;
         rc = tconv_mma_wgrad(g, dyo, xo, dW, dbias, st);           // small-channel temporal convolutions (tconv_mma.cu)
         if (rc != 0) return rc < 0 ? rc : 0;

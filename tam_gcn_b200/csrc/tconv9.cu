@@ -457,7 +457,8 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
 #define W9_DRAIN_PITCH (32 * T9_MAXK * 4 + 16)    // staging row of the drain: 288 floats + 16 B (bank spread)
 
 struct W9P {
-    int N, Cin, Cout, T, k, pad;
+    int N, Cin, Cout, T, k, pad;                  // T = input time steps
+    int To, stride, ts;                           // output time steps; dY time steps per stage (8, stride 2: 4)
     int n_cot, n_cit, n_seg, seg_stages;          // item = ((n * n_seg + seg) * n_cot + cot) * n_cit + cit
     uint32_t off_hdr;
 };
@@ -489,7 +490,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
     const int n = item / p.n_seg;
     const int NB = min(32, p.Cin - cit * 32);                     // input channels of this tile (16 or 32)
     const int stage0 = seg * p.seg_stages;
-    const int n_st = min(p.seg_stages, (p.T + W9_TS - 1) / W9_TS - stage0);
+    const int n_st = min(p.seg_stages, (p.To + p.ts - 1) / p.ts - stage0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < W9_S; ++s) { mbar_init(&hdr->full[s], T9_LD_W); mbar_init(&hdr->empty[s], 1); }
@@ -513,12 +514,12 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
                 if (!mbar_wait_spin(&hdr->full[stg], (uint32_t)ph)) { hdr->error = 1; ok = false; break; }
                 tc_fence_after();
                 const uint32_t sa = s0 + (uint32_t)stg * W9_STAGE_BYTES, sb = sa + W9_A_BYTES;
-                for (int tau = 0; tau < W9_TS; ++tau) {
+                for (int tau = 0; tau < p.ts; ++tau) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint64_t ad = umma_desc_sw128(sa + (uint32_t)(tau >> 1) * 16384u + (uint32_t)((tau & 1) * 64 + h * 32));
                         for (int j = 0; j < p.k; ++j) {
-                            const int sx = tau + j;                       // X time-step slot of the stage
+                            const int sx = p.stride * tau + j;            // X time-step slot of the stage
                             const uint64_t bd = umma_desc_sw128(sb + (uint32_t)(sx >> 1) * 4096u + (uint32_t)((sx & 1) * 64 + h * 32));
                             umma_bf16(tmem + (uint32_t)(j * 32), ad, bd, idesc, (st > 0 || tau > 0 || h > 0) ? 1u : 0u);
                         }
@@ -577,17 +578,17 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
         auto request = [&]() {
             nkind = 0;
             if (l_st >= n_st) return;
-            const int t_stage = (stage0 + l_st) * W9_TS;
+            const int t_stage = (stage0 + l_st) * p.ts;
             if (l_q < 3) {
                 const int step = a_s0 + 3 * l_q;
-                if (step < W9_TS) {
+                if (step < p.ts) {
                     const int t = t_stage + step;
                     ndsto = (uint32_t)(step >> 1) * 16384u + (uint32_t)a_co * 128u + (uint32_t)(step & 1) * 64u;
                     nrsw = (uint32_t)a_co & 7u;
                     nkind = 1;
-                    if (a_chv && t < p.T) {
+                    if (a_chv && t < p.To) {
                         nkind = 2;
-                        const long long e = ((long long)cha * p.T + t) * V;
+                        const long long e = ((long long)cha * p.To + t) * V;
                         {
                             const uintptr_t a = reinterpret_cast<uintptr_t>((const bf16*)dy.p + (long long)n * dy.pns + e);
                             nsftp = (uint32_t)(a & 15);
@@ -607,7 +608,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
                 if (idx < 512) {
                     const int cl = idx & 31, sx = idx >> 5;
                     if (cl < NB) {
-                        const int t = t_stage - p.pad + sx, ci = cit * 32 + cl;
+                        const int t = t_stage * p.stride - p.pad + sx, ci = cit * 32 + cl;
                         ndsto = W9_A_BYTES + (uint32_t)(sx >> 1) * 4096u + (uint32_t)cl * 128u + (uint32_t)(sx & 1) * 64u;
                         nrsw = (uint32_t)cl & 7u;
                         nkind = 1;
@@ -770,19 +771,21 @@ int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int To, int V, int 
 }
 
 // returns 1 if launched, 0 if not covered, < 0 on error
-int tconv9_wgrad_launch(int N, int Cin, int Cout, int T, int V, int k, int stride, int dil, int pad, const Opnd& dy, const Opnd& x,
-                        float* dW, float* db, cudaStream_t st) {
+int tconv9_wgrad_launch(int N, int Cin, int Cout, int T, int To, int V, int k, int stride, int dil, int pad, const Opnd& dy,
+                        const Opnd& x, float* dW, float* db, cudaStream_t st) {
     if (t9_disabled()) return 0;
     static const bool off = [] { const char* e = getenv("TAMGCN_DISABLE_T9W"); return e && e[0] == '1'; }();
     if (off) return 0;
-    if (!(V == T9_V && stride == 1 && dil == 1 && 2 * pad == k - 1 && k >= 2 && k <= T9_MAXK && Cin % 16 == 0 && Cin >= 32 && Cout >= 32))
-        return 0;
+    const bool geom = (stride == 1 && 2 * pad == k - 1 && k >= 2) || (stride == 2 && ((k == 9 && pad == 4) || (k == 1 && pad == 0)));
+    if (!(V == T9_V && dil == 1 && geom && k <= T9_MAXK && Cin % 16 == 0 && Cin >= 32 && Cout >= 32)) return 0;
+    if ((Cin * k) % 4) return 0;                           // vector reductions of the drain
     if (x.q) return 0;                                     // the X operand is a one-tensor lazy operand
     if ((reinterpret_cast<uintptr_t>(dW) & 15) != 0) return 0;
     W9P p = {};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.T = T; p.k = k; p.pad = pad;
+    p.To = To; p.stride = stride; p.ts = stride == 1 ? W9_TS : 4;
     p.n_cot = (Cout + 127) / 128; p.n_cit = (Cin + 31) / 32;
-    const int stages = (T + W9_TS - 1) / W9_TS;
+    const int stages = (To + p.ts - 1) / p.ts;
     // segments per sample: enough items for ~2.5 waves of CTAs, at least 4 stages per item
     const long long base_items = (long long)N * p.n_cot * p.n_cit;
     int n_seg = (int)((5LL * wgrad_sms() / 2 + base_items - 1) / base_items);
