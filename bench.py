@@ -397,9 +397,9 @@ def measured_peaks():
 # step-level roofline: device time per kernel family (CUPTI) against the algorithmic bytes / FLOPs of the step
 # ------------------------------------------------------------------------------------------------------------
 FAMILIES = [
-    ('conv_wgrad', r'conv_wg2_kernel|tconv_wgrad_mma_kernel|conv_wgrad_kernel|conv_wgrad_tc_kernel|smallL_wgrad'),
-    ('conv_dgrad', r'conv_tc2_kernel<\(int\)1|conv_tc2_kernel<1|conv_dgrad|tconv_mma_kernel.*dgrad|smallL_dgrad'),
-    ('conv_fwd', r'conv_tc2_kernel|tconv_mma_kernel|conv_fwd|smallL_fwd|pack_w2'),
+    ('conv_wgrad', r'conv_wg2_kernel|tconv_wgrad_mma_kernel|conv_wgrad_kernel|conv_wgrad_tc_kernel|smallL_wgrad|tconv9_wgrad'),
+    ('conv_dgrad', r'conv_tc2_kernel<\(int\)1|conv_tc2_kernel<1|conv_dgrad|tconv_mma_kernel.*dgrad|smallL_dgrad|tconv9_kernel<\(int\)1|tconv9_kernel<1'),
+    ('conv_fwd', r'conv_tc2_kernel|tconv_mma_kernel|conv_fwd|smallL_fwd|pack_w2|tconv9_kernel'),
     ('ctrgc_bwd', r'ctrgc_bwd'),
     ('ctrgc_fwd', r'ctrgc_fwd'),
     ('epilogues+maxpool', r'epilogue|maxpool|gcn_mid|mean_t'),

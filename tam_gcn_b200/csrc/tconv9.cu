@@ -134,7 +134,7 @@ __device__ __forceinline__ void t9_stage_row(unsigned char* row, int E, const ui
     }
 }
 
-template <bool HASQ>
+template <int MODE, bool HASQ>
 __global__ void __launch_bounds__(T9_THREADS, 1)
 tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __restrict__ out, T9Epi ep) {
     extern __shared__ unsigned char t9_smem[];
@@ -223,7 +223,7 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
             const int chw = mt * 128 + q * 32, ch = chw + lane;
             const bool chv = ch < p.OC;
             if (chw < p.OC) {
-                const float bias_ = (p.mode == 0 && ep.bias && chv) ? __ldg(ep.bias + ch) : 0.f;
+                const float bias_ = (MODE == 0 && ep.bias && chv) ? __ldg(ep.bias + ch) : 0.f;
                 float ma_ = 1.f, mc_ = 0.f;
                 if (ep.has_mask && chv) {
                     if (ep.maska) ma_ = __ldg(ep.maska + ch);
@@ -245,7 +245,7 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
                         const int col = (p.var == 2) ? ((sg & 1) * 256 + (sg >> 1) * 32) : sg * 32;
                         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, acc);
                         uint32_t W[13];
-                        if (p.mode == 0) {
+                        if (MODE == 0) {
 #pragma unroll
                             for (int i = 0; i < 13; ++i) {
                                 const uint32_t w = pack_bf16(acc[2 * i] + bias_, (2 * i + 1 < V) ? acc[2 * i + 1] + bias_ : 0.f);
@@ -756,15 +756,15 @@ int tconv9_launch(int mode, int N, int Cin, int Cout, int T, int To, int V, int 
     if (mask) { ep.has_mask = 1; ep.maskp = (const bf16*)mask->p; ep.maskns = mask->pns; ep.maska = mask->a; ep.maskc = mask->c; }
     int grid = main_sms();
     if (grid > p.n_tiles) grid = p.n_tiles;
-    if (in.q) {
-        static SmemLimit lim;
-        ensure_smem(tconv9_kernel<true>, lim, sm);
-        tconv9_kernel<true><<<grid, T9_THREADS, sm, st>>>(p, in, (const unsigned char*)wpack9, (bf16*)out, ep);
-    } else {
-        static SmemLimit lim;
-        ensure_smem(tconv9_kernel<false>, lim, sm);
-        tconv9_kernel<false><<<grid, T9_THREADS, sm, st>>>(p, in, (const unsigned char*)wpack9, (bf16*)out, ep);
-    }
+#define T9_LAUNCH(MM, QQ)                                                                                                   \
+    do {                                                                                                                    \
+        static SmemLimit lim;                                                                                               \
+        ensure_smem(tconv9_kernel<MM, QQ>, lim, sm);                                                                        \
+        tconv9_kernel<MM, QQ><<<grid, T9_THREADS, sm, st>>>(p, in, (const unsigned char*)wpack9, (bf16*)out, ep);           \
+    } while (0)
+    if (mode == 0) { if (in.q) T9_LAUNCH(0, true); else T9_LAUNCH(0, false); }
+    else           { if (in.q) T9_LAUNCH(1, true); else T9_LAUNCH(1, false); }
+#undef T9_LAUNCH
     count_launch();
     const int rc = check_launch(mode ? "conv_dgrad(tconv9)" : "conv_fwd(tconv9)");
     return rc < 0 ? rc : 1;
