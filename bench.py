@@ -582,7 +582,9 @@ def main():
             roof_bwd = ctrgc_roofline(dtype, peak, peak_src, 2048, 64, 52, 20, 3, 8, backward=True, tag='ctrgc_bwd_ucla_2048')
             # the cfg4 size, batch 1024 -> N'=2048, l2-l4: C=64, T=64, V=25
             roof_ntu = ctrgc_roofline(dtype, peak, peak_src, 2048, 64, 64, 25, 3, 8, tag='ctrgc_fwd_ntu_2048')
-        if not args.no_step_roofline and runner.graph is not None:
+        # (single GPU only: with N > 1 the step graph holds the all-reduce, and replaying it on rank 0 alone would wait
+        # for the other ranks forever)
+        if not args.no_step_roofline and runner.graph is not None and world == 1:
             try:
                 roof_step = step_roofline(runner.graph.replay, acct, 5, peak, peak_tf, ms_per_step)
             except Exception as e:  # noqa: BLE001
