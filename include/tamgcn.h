@@ -196,7 +196,8 @@ int tamgcn_maxpool_bwd(int dtype, int N, int C, int T, int To, int V, int stride
 int tamgcn_graph_agg_fwd(int dtype, int N, int K, int C, int T, int V, const void* y, int64_t y_nstride,
                          const float* A, void* out, int64_t out_nstride, double* stat_sum, double* stat_sumsq,
                          tamgcn_stream stream);
-/* dy[n,k*C+c,t,v] = sum_w dOut(n,c,t,w) A[k,v,w];  dA[k,v,w] += sum_{n,c,t} y[n,k*C+c,t,v] dOut(n,c,t,w) */
+/* dy[n,k*C+c,t,v] = sum_w dOut(n,c,t,w) A[k,v,w];  dA[k,v,w] += sum_{n,c,t} y[n,k*C+c,t,v] dOut(n,c,t,w).
+ * dy or dA may be NULL (the other half only): dA feeds nothing but the optimiser, so a step engine runs it apart. */
 int tamgcn_graph_agg_bwd(int dtype, int N, int K, int C, int T, int V, const tamgcn_operand* dout, const void* y,
                          int64_t y_nstride, const float* A, void* dy, int64_t dy_nstride, float* dA,
                          tamgcn_stream stream);

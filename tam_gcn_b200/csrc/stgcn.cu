@@ -198,7 +198,7 @@ extern "C" int tamgcn_graph_agg_fwd(int dtype, int N, int K, int C, int T, int V
 extern "C" int tamgcn_graph_agg_bwd(int dtype, int N, int K, int C, int T, int V, const tamgcn_operand* dout,
                                     const void* y, int64_t y_nstride, const float* A, void* dy, int64_t dy_nstride,
                                     float* dA, tamgcn_stream stream) {
-    TG_REQUIRE(N > 0 && K > 0 && C > 0 && T > 0 && dout && dout->p && A && dy, "graph_agg_bwd: bad arguments");
+    TG_REQUIRE(N > 0 && K > 0 && C > 0 && T > 0 && dout && dout->p && A && (dy || dA), "graph_agg_bwd: bad arguments");
     TG_REQUIRE(V == 20 || V == 25, "graph_agg_bwd: V=%d not supported (20 or 25)", V);
     TG_REQUIRE(!dA || y, "graph_agg_bwd: dA needs y");
     TG_REQUIRE(K * V * V <= AGG_MAXACC * 256, "graph_agg_bwd: K*V*V=%d too large", K * V * V);
@@ -211,12 +211,14 @@ extern "C" int tamgcn_graph_agg_bwd(int dtype, int N, int K, int C, int T, int V
     }
     const size_t sm = sizeof(float) * K * V * ((V + 3) & ~3);
 #define AGG_DY(T_, V_) graph_agg_dy_kernel<T_, V_><<<grid, 256, sm, st>>>(N, K, C, T, go, A, (T_*)dy, dy_nstride)
-    if (dtype == TAMGCN_F32) { if (V == 20) AGG_DY(float, 20); else AGG_DY(float, 25); }
-    else if (dtype == TAMGCN_BF16) { if (V == 20) AGG_DY(bf16, 20); else AGG_DY(bf16, 25); }
-    else return set_error("graph_agg_bwd: bad dtype %d", dtype);
+    if (dtype != TAMGCN_F32 && dtype != TAMGCN_BF16) return set_error("graph_agg_bwd: bad dtype %d", dtype);
+    if (dy) {
+        if (dtype == TAMGCN_F32) { if (V == 20) AGG_DY(float, 20); else AGG_DY(float, 25); }
+        else { if (V == 20) AGG_DY(bf16, 20); else AGG_DY(bf16, 25); }
+        count_launch();
+        if (check_launch("graph_agg_bwd(dy)")) return -2;
+    }
 #undef AGG_DY
-    count_launch();
-    if (check_launch("graph_agg_bwd(dy)")) return -2;
     if (dA) {
         const size_t sm2 = sizeof(float) * AGG_RB * (K * V + V);
         if (dtype == TAMGCN_F32)

@@ -488,7 +488,7 @@ int graph_agg_bwd_mma(int N, int K, int C, int T, int V, const Opnd& go, const v
         return 0;
     SgP p = {N, K, C, T, yns, dyns, N * C, (T + 15) / 16};
     const size_t sgb = V == 20 ? SgCfg<20>::SGB : SgCfg<25>::SGB;
-    {
+    if (dy) {
         const size_t sm = (size_t)SG_WARPS * 5 * sgb;
         const int grid = sg_grid(p, sm);
 #define SG_DY(VV, KK)                                                                                                  \

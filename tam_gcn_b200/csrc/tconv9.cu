@@ -106,6 +106,26 @@ __device__ __forceinline__ void t9_load_row(const bf16* rowp, uint4 (&c)[3], uin
         e24 = (sft & 2u) ? (w >> 16) : (w & 0xffffu);
     }
 }
+// the same in two halves: request the granules early, split when the values are needed
+__device__ __forceinline__ uint32_t t9_row_request(const bf16* rowp, uint4 (&w)[4]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(rowp);
+    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    w[0] = __ldg(q); w[1] = __ldg(q + 1); w[2] = __ldg(q + 2); w[3] = __ldg(q + 3);
+    return (uint32_t)(a & 15);
+}
+__device__ __forceinline__ void t9_row_split(const uint4 (&w)[4], uint32_t sft, uint4 (&c)[3], uint32_t& e24) {
+    if (sft == 0) {
+        c[0] = w[0]; c[1] = w[1]; c[2] = w[2];
+        e24 = w[3].x & 0xffffu;
+    } else {
+        c[0] = tc_realign16(w[0], w[1], sft);
+        c[1] = tc_realign16(w[1], w[2], sft);
+        c[2] = tc_realign16(w[2], w[3], sft);
+        const uint32_t ws = sft >> 2;
+        const uint32_t ww = ws == 0 ? w[3].x : (ws == 1 ? w[3].y : (ws == 2 ? w[3].z : w[3].w));
+        e24 = (sft & 2u) ? (ww >> 16) : (ww & 0xffffu);
+    }
+}
 __device__ __forceinline__ float t9_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float t9_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ uint32_t t9_xf2(uint32_t p, uint32_t q, const OpCoef& cf, bool has_q, bool relu) {
