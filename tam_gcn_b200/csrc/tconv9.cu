@@ -479,6 +479,8 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
 struct W9P {
     int N, Cin, Cout, T, k, pad;                  // T = input time steps
     int To, stride, ts;                           // output time steps; dY time steps per stage (8, stride 2: 4)
+    int nbmax, nslots;                            // input channels per tile (32; k = 1: 256); X time-step slots per stage
+    uint32_t a_bytes;                             // dY part of a stage (the X part follows)
     int n_cot, n_cit, n_seg, seg_stages;          // item = ((n * n_seg + seg) * n_cot + cot) * n_cit + cit
     uint32_t off_hdr;
 };
@@ -508,7 +510,8 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
     const int cot = item % p.n_cot; item /= p.n_cot;
     const int seg = item % p.n_seg;
     const int n = item / p.n_seg;
-    const int NB = min(32, p.Cin - cit * 32);                     // input channels of this tile (16 or 32)
+    const int NBM = p.nbmax;
+    const int NB = min(NBM, p.Cin - cit * NBM);                   // input channels of this tile
     const int stage0 = seg * p.seg_stages;
     const int n_st = min(p.seg_stages, (p.To + p.ts - 1) / p.ts - stage0);
 
@@ -533,15 +536,15 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
             for (int st = 0; st < n_st && ok; ++st) {
                 if (!mbar_wait_spin(&hdr->full[stg], (uint32_t)ph)) { hdr->error = 1; ok = false; break; }
                 tc_fence_after();
-                const uint32_t sa = s0 + (uint32_t)stg * W9_STAGE_BYTES, sb = sa + W9_A_BYTES;
+                const uint32_t sa = s0 + (uint32_t)stg * W9_STAGE_BYTES, sb = sa + p.a_bytes;
                 for (int tau = 0; tau < p.ts; ++tau) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint64_t ad = umma_desc_sw128(sa + (uint32_t)(tau >> 1) * 16384u + (uint32_t)((tau & 1) * 64 + h * 32));
                         for (int j = 0; j < p.k; ++j) {
                             const int sx = p.stride * tau + j;            // X time-step slot of the stage
-                            const uint64_t bd = umma_desc_sw128(sb + (uint32_t)(sx >> 1) * 4096u + (uint32_t)((sx & 1) * 64 + h * 32));
-                            umma_bf16(tmem + (uint32_t)(j * 32), ad, bd, idesc, (st > 0 || tau > 0 || h > 0) ? 1u : 0u);
+                            const uint64_t bd = umma_desc_sw128(sb + (uint32_t)(sx >> 1) * (uint32_t)(NBM * 128) + (uint32_t)((sx & 1) * 64 + h * 32));
+                            umma_bf16(tmem + (uint32_t)(j * NBM), ad, bd, idesc, (st > 0 || tau > 0 || h > 0) ? 1u : 0u);
                         }
                     }
                 }
@@ -558,12 +561,15 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
             const int co = q * 32 + lane;
             unsigned char* rowp = sbase + (size_t)co * W9_DRAIN_PITCH;
             const int rowlen = NB * p.k;                             // floats of a dW row segment of this tile
-            for (int j = hh; j < p.k; j += 2) {
+            // 32-column groups of the k * NBM accumulator columns: column = j * NBM + ci
+            for (int gcol = hh; gcol * 32 < p.k * NBM; gcol += 2) {
+                const int j = (gcol * 32) / NBM, c0 = gcol * 32 - j * NBM;
+                if (c0 >= NB) continue;
                 float acc[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 32), acc);
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(gcol * 32), acc);
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                    if (c < NB) reinterpret_cast<float*>(rowp)[c * p.k + j] = acc[c];
+                    if (c0 + c < NB) reinterpret_cast<float*>(rowp)[(c0 + c) * p.k + j] = acc[c];
             }
             // both warps of a quarter must have written their taps before rows are read back
             asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
@@ -572,7 +578,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
                 const int cor = cot * 128 + q * 32 + r;
                 if (cor >= p.Cout) break;
                 const unsigned char* src = sbase + (size_t)(q * 32 + r) * W9_DRAIN_PITCH;
-                float* dst = dW + ((long long)cor * p.Cin + cit * 32) * p.k;
+                float* dst = dW + ((long long)cor * p.Cin + cit * NBM) * p.k;
                 for (int i = lane; i < nv4; i += 32) red_add_v4(dst + 4 * i, *reinterpret_cast<const float4*>(src + 16 * i));
             }
         }
@@ -594,12 +600,14 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
         uint32_t dsto = 0, ndsto = 0;         // byte offset of the row (chunk 0, unswizzled) inside the stage
         uint32_t rsw = 0, nrsw = 0;           // row & 7 (swizzle key)
         OpCoef cfb = {1.f, 0.f, 0.f}, ncfb = {1.f, 0.f, 0.f};
+        const int nA = (128 * p.ts + 383) / 384;                       // A-row slots per thread and stage; the B-row slots follow
+        const int nQ = nA + (NBM * p.nslots + 383) / 384;
         int l_st = 0, l_q = 0;                // (stage, slot) to request next
         auto request = [&]() {
             nkind = 0;
             if (l_st >= n_st) return;
             const int t_stage = (stage0 + l_st) * p.ts;
-            if (l_q < 3) {
+            if (l_q < nA) {
                 const int step = a_s0 + 3 * l_q;
                 if (step < p.ts) {
                     const int t = t_stage + step;
@@ -624,12 +632,12 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
                     }
                 }
             } else {
-                const int idx = ltid + 384 * (l_q - 3);
-                if (idx < 512) {
-                    const int cl = idx & 31, sx = idx >> 5;
+                const int idx = ltid + 384 * (l_q - nA);
+                if (idx < NBM * p.nslots) {
+                    const int cl = idx % NBM, sx = idx / NBM;
                     if (cl < NB) {
-                        const int t = t_stage * p.stride - p.pad + sx, ci = cit * 32 + cl;
-                        ndsto = W9_A_BYTES + (uint32_t)(sx >> 1) * 4096u + (uint32_t)cl * 128u + (uint32_t)(sx & 1) * 64u;
+                        const int t = t_stage * p.stride - p.pad + sx, ci = cit * NBM + cl;
+                        ndsto = p.a_bytes + (uint32_t)(sx >> 1) * (uint32_t)(NBM * 128) + (uint32_t)cl * 128u + (uint32_t)(sx & 1) * 64u;
                         nrsw = (uint32_t)cl & 7u;
                         nkind = 1;
                         if (t >= 0 && t < p.T) {
@@ -644,7 +652,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
                 }
             }
         };
-        auto advance = [&]() { if (++l_q == 5) { l_q = 0; ++l_st; } };
+        auto advance = [&]() { if (++l_q == nQ) { l_q = 0; ++l_st; } };
         auto split = [&](const uint4* w, uint32_t sft, uint4 (&c)[3], uint32_t& e24) {
             if (sft == 0) {
                 c[0] = w[0]; c[1] = w[1]; c[2] = w[2];
@@ -663,7 +671,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
         request();
         advance();
         for (int st = 0; st < n_st && ok; ++st) {
-            for (int qslot = 0; qslot < 5; ++qslot) {
+            for (int qslot = 0; qslot < nQ; ++qslot) {
                 kind = nkind; dsto = ndsto; rsw = nrsw; sftp = nsftp; sftq = nsftq; cfb = ncfb;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { pw[i] = npw[i]; if (HASQ) qw[i] = nqw[i]; }
@@ -796,15 +804,22 @@ int tconv9_wgrad_launch(int N, int Cin, int Cout, int T, int To, int V, int k, i
     if (t9_disabled()) return 0;
     static const bool off = [] { const char* e = getenv("TAMGCN_DISABLE_T9W"); return e && e[0] == '1'; }();
     if (off) return 0;
-    const bool geom = (stride == 1 && 2 * pad == k - 1 && k >= 2) || (stride == 2 && ((k == 9 && pad == 4) || (k == 1 && pad == 0)));
+    // k = 1, stride 1 only where the vector-access kernel (conv_wg2.cu) has no aligned path: planes of T*V elements that
+    // are not a multiple of 4 (ST-GCN T = 150 / 75 at V = 25)
+    const bool geom = (stride == 1 && 2 * pad == k - 1 && (k >= 2 || ((long long)T * V) % 4 != 0)) ||
+                      (stride == 2 && ((k == 9 && pad == 4) || (k == 1 && pad == 0)));
     if (!(V == T9_V && dil == 1 && geom && k <= T9_MAXK && Cin % 16 == 0 && Cin >= 32 && Cout >= 32)) return 0;
     if ((Cin * k) % 4) return 0;                           // vector reductions of the drain
     if (x.q) return 0;                                     // the X operand is a one-tensor lazy operand
     if ((reinterpret_cast<uintptr_t>(dW) & 15) != 0) return 0;
     W9P p = {};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.T = T; p.k = k; p.pad = pad;
-    p.To = To; p.stride = stride; p.ts = stride == 1 ? W9_TS : 4;
-    p.n_cot = (Cout + 127) / 128; p.n_cit = (Cin + 31) / 32;
+    p.To = To; p.stride = stride; p.ts = (stride == 1 && k > 1) ? W9_TS : 4;
+    p.nbmax = (k == 1 && stride == 1) ? 256 : 32;                    // one tap leaves room for 256 accumulator columns
+    p.nslots = (stride * (p.ts - 1) + k + 1) & ~1;
+    p.a_bytes = (uint32_t)(p.ts / 2) * 16384u;
+    if (p.a_bytes + (uint32_t)(p.nslots / 2) * (uint32_t)(p.nbmax * 128) > W9_STAGE_BYTES) return 0;
+    p.n_cot = (Cout + 127) / 128; p.n_cit = (Cin + p.nbmax - 1) / p.nbmax;
     const int stages = (To + p.ts - 1) / p.ts;
     // segments per sample: enough items for ~2.5 waves of CTAs, at least 4 stages per item
     const long long base_items = (long long)N * p.n_cot * p.n_cit;

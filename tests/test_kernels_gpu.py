@@ -74,7 +74,9 @@ CONV_GEOMS = [  # (Cin, Cout, T, k, s, d)
     # the ST-GCN temporal convolutions served (at V = 25) by the V-padded tcgen05 kernel (tconv9.cu)
     (64, 64, 40, 9, 1, 1), (128, 64, 35, 9, 1, 1), (64, 128, 75, 5, 1, 1), (256, 256, 19, 9, 1, 1), (64, 64, 300, 9, 1, 1),
     # ... and the stride-2 layers (l5, l8)
-    (64, 64, 40, 9, 2, 1), (128, 128, 75, 9, 2, 1), (64, 128, 31, 9, 2, 1)]
+    (64, 64, 40, 9, 2, 1), (128, 128, 75, 9, 2, 1), (64, 128, 31, 9, 2, 1),
+    # 1x1 graph convolutions on planes of odd length (T*V % 4 != 0 at V = 25): weight gradient through tconv9's k = 1 tiles
+    (64, 192, 75, 1, 1, 1), (256, 96, 30, 1, 1, 1)]
 
 
 def _pad(k, d):
