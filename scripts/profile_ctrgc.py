@@ -26,6 +26,8 @@ if len(sys.argv) > 2 and sys.argv[2] == 'ntu_l9':
     N, Cout, T, V, K, R = 512, 256, 16, 25, 3, 32
 if len(sys.argv) > 2 and sys.argv[2] == 'ntu_l9_64':
     N, Cout, T, V, K, R = 64, 256, 16, 25, 3, 32
+if len(sys.argv) > 2 and sys.argv[2] == 'ntu2048':
+    N, Cout, T, V, K, R = 2048, 64, 64, 25, 3, 8
 dev = 'cuda'
 g = torch.Generator(device='cuda').manual_seed(0)
 x3 = torch.randn(N, K * Cout, T, V, device=dev, generator=g).to(dtype)
