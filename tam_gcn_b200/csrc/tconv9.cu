@@ -474,6 +474,8 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
 #define W9_B_BYTES (8 * 32 * 128)                 // 8 K blocks x 32 rows x 128 B
 #define W9_STAGE_BYTES (W9_A_BYTES + W9_B_BYTES)  // 96 KB
 #define W9_S 2
+#define W9_LD_WARPS 16                           // loader warps: 8-19 and 4-7
+#define W9_LT (W9_LD_WARPS * 32)
 #define W9_DRAIN_PITCH (32 * T9_MAXK * 4 + 16)    // staging row of the drain: 288 floats + 16 B (bank spread)
 
 struct W9P {
@@ -516,7 +518,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
     const int n_st = min(p.seg_stages, (p.To + p.ts - 1) / p.ts - stage0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < W9_S; ++s) { mbar_init(&hdr->full[s], T9_LD_W); mbar_init(&hdr->empty[s], 1); }
+        for (int s = 0; s < W9_S; ++s) { mbar_init(&hdr->full[s], W9_LD_WARPS); mbar_init(&hdr->empty[s], 1); }
         mbar_init(&hdr->done, 1);
         hdr->error = 0;
         fence_mbar_init();
@@ -527,7 +529,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
     tc_fence_after();
     const uint32_t tmem = hdr->tmem_base;
 
-    if (warp < T9_EPI_W) {
+    if (warp < 4) {
         if (warp == 0 && lane == 0) {
             // ---- MMA issue ----
             const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)NB);
@@ -554,41 +556,14 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
             if (ok) umma_commit(&hdr->done);
         }
         __syncwarp();
-        // ---- drain ----
-        if (t9_wait(hdr, &hdr->done, 0u)) {
-            tc_fence_after();
-            const int q = warp & 3, hh = warp >> 2;                  // lane quarter; the two warps of a quarter split the taps
-            const int co = q * 32 + lane;
-            unsigned char* rowp = sbase + (size_t)co * W9_DRAIN_PITCH;
-            const int rowlen = NB * p.k;                             // floats of a dW row segment of this tile
-            // 32-column groups of the k * NBM accumulator columns: column = j * NBM + ci
-            for (int gcol = hh; gcol * 32 < p.k * NBM; gcol += 2) {
-                const int j = (gcol * 32) / NBM, c0 = gcol * 32 - j * NBM;
-                if (c0 >= NB) continue;
-                float acc[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(gcol * 32), acc);
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (c0 + c < NB) reinterpret_cast<float*>(rowp)[(c0 + c) * p.k + j] = acc[c];
-            }
-            // both warps of a quarter must have written their taps before rows are read back
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
-            const int nv4 = rowlen / 4;                              // NB * k is a multiple of 4 (NB = 16 / 32)
-            for (int r = hh; r < 32; r += 2) {
-                const int cor = cot * 128 + q * 32 + r;
-                if (cor >= p.Cout) break;
-                const unsigned char* src = sbase + (size_t)(q * 32 + r) * W9_DRAIN_PITCH;
-                float* dst = dW + ((long long)cor * p.Cin + cit * NBM) * p.k;
-                for (int i = lane; i < nv4; i += 32) red_add_v4(dst + 4 * i, *reinterpret_cast<const float4*>(src + 16 * i));
-            }
-        }
     } else {
         // =============================== loaders ===============================
-        const int ltid = threadIdx.x - T9_LD_W0 * 32;
+        // 512 loader threads: warps 8-19 and the second drain group (warps 4-7), which is idle until the drain
+        const int ltid = warp >= T9_EPI_W ? (int)threadIdx.x - T9_EPI_W * 32 : 384 + (int)threadIdx.x - 128;
         constexpr bool has_q = HASQ;
         const bool lazy_a = dy.a || dy.c || has_q || dy.relu, relu_a = dy.relu != 0;
         const bool lazy_b = x.a || x.c || x.relu, relu_b = x.relu != 0;
-        // slots of this thread in a stage: A rows (co = ltid & 127, steps (ltid >> 7) + 3 i), B rows (idx = ltid + 384 i)
+        // slots of this thread in a stage: A rows (co = ltid & 127, steps (ltid >> 7) + 4 i), B rows (idx = ltid + 512 i)
         const int a_co = ltid & 127, a_s0 = ltid >> 7;
         const int cha = cot * 128 + a_co;
         const bool a_chv = cha < p.Cout;
@@ -600,15 +575,15 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
         uint32_t dsto = 0, ndsto = 0;         // byte offset of the row (chunk 0, unswizzled) inside the stage
         uint32_t rsw = 0, nrsw = 0;           // row & 7 (swizzle key)
         OpCoef cfb = {1.f, 0.f, 0.f}, ncfb = {1.f, 0.f, 0.f};
-        const int nA = (128 * p.ts + 383) / 384;                       // A-row slots per thread and stage; the B-row slots follow
-        const int nQ = nA + (NBM * p.nslots + 383) / 384;
+        const int nA = (128 * p.ts + W9_LT - 1) / W9_LT;                // A-row slots per thread and stage; the B-row slots follow
+        const int nQ = nA + (NBM * p.nslots + W9_LT - 1) / W9_LT;
         int l_st = 0, l_q = 0;                // (stage, slot) to request next
         auto request = [&]() {
             nkind = 0;
             if (l_st >= n_st) return;
             const int t_stage = (stage0 + l_st) * p.ts;
             if (l_q < nA) {
-                const int step = a_s0 + 3 * l_q;
+                const int step = a_s0 + 4 * l_q;
                 if (step < p.ts) {
                     const int t = t_stage + step;
                     ndsto = (uint32_t)(step >> 1) * 16384u + (uint32_t)a_co * 128u + (uint32_t)(step & 1) * 64u;
@@ -632,7 +607,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
                     }
                 }
             } else {
-                const int idx = ltid + 384 * (l_q - nA);
+                const int idx = ltid + W9_LT * (l_q - nA);
                 if (idx < NBM * p.nslots) {
                     const int cl = idx % NBM, sx = idx / NBM;
                     if (cl < NB) {
@@ -728,6 +703,36 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
             if (++stg == W9_S) { stg = 0; ph ^= 1; }
         }
         if (db && cit == 0 && a_chv && dbsum != 0.f) atomicAdd(db + cha, dbsum);
+    }
+    if (warp < T9_EPI_W) {
+        // ---- drain (warps 4-7 come here after their loader duty) ----
+        if (t9_wait(hdr, &hdr->done, 0u)) {
+            tc_fence_after();
+            const int q = warp & 3, hh = warp >> 2;                  // lane quarter; the two warps of a quarter split the taps
+            const int co = q * 32 + lane;
+            unsigned char* rowp = sbase + (size_t)co * W9_DRAIN_PITCH;
+            const int rowlen = NB * p.k;                             // floats of a dW row segment of this tile
+            // 32-column groups of the k * NBM accumulator columns: column = j * NBM + ci
+            for (int gcol = hh; gcol * 32 < p.k * NBM; gcol += 2) {
+                const int j = (gcol * 32) / NBM, c0 = gcol * 32 - j * NBM;
+                if (c0 >= NB) continue;
+                float acc[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(gcol * 32), acc);
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c0 + c < NB) reinterpret_cast<float*>(rowp)[(c0 + c) * p.k + j] = acc[c];
+            }
+            // both warps of a quarter must have written their taps before rows are read back
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(64) : "memory");
+            const int nv4 = rowlen / 4;                              // NB * k is a multiple of 4 (NB = 16 / 32)
+            for (int r = hh; r < 32; r += 2) {
+                const int cor = cot * 128 + q * 32 + r;
+                if (cor >= p.Cout) break;
+                const unsigned char* src = sbase + (size_t)(q * 32 + r) * W9_DRAIN_PITCH;
+                float* dst = dW + ((long long)cor * p.Cin + cit * NBM) * p.k;
+                for (int i = lane; i < nv4; i += 32) red_add_v4(dst + 4 * i, *reinterpret_cast<const float4*>(src + 16 * i));
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
