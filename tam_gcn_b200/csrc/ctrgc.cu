@@ -13,6 +13,7 @@
 //
 // SIMT fp32 math for both storage types.  V is a template parameter (20 = NW-UCLA, 25 = NTU).
 #include "common.cuh"
+#include <cstdio>
 #include <type_traits>
 #include "rows.cuh"
 #include <atomic>
@@ -387,6 +388,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
 //   dD[r,uv]   = sum_c W4[c,r] dQ[c,uv]         -> dS = alpha dD (1 - D^2) -> dx1, dx2
 // LEAN (large R: the full tables do not fit 227 KB): the fp32 tanh table is not kept — the last phase recomputes
 // tanh from x1/x2 (same instruction, same value) and stages dS for 16 rows of r at a time.
+__device__ int g_cbm_dbg = 0;        // TAMGCN_CBM_DBG=1: block (0,0) prints its cycles per phase
+
 template <int V, bool LEAN>
 __global__ void __launch_bounds__(CBM_THREADS)
 ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float* __restrict__ x1,
@@ -425,6 +428,8 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
     __syncthreads();
     for (int idx = tid; idx < UV; idx += CBM_THREADS) Db[R * UP + idx] = one;
     float dalpha_acc = 0.f;
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tmark = clock64();
+#define CBM_MARK(ix) do { if (g_cbm_dbg) { const long long t_ = clock64(); tph[ix] += t_ - tmark; tmark = t_; } } while (0)
 
     for (int i = 0; i < K; ++i) {
         __syncthreads();
@@ -468,6 +473,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
             }
         }
         __syncthreads();
+        CBM_MARK(0);
         // ---- Q = alpha (W4 . D + b4) + PA, as Qt[c][v][u] (bf16) ----
         for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
             float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -494,6 +500,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
             }
         }
         __syncthreads();
+        CBM_MARK(1);
 
         // ---- per channel (one warp each): dx3 and dQ ----
         if (warp < nc) {
@@ -627,6 +634,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                     }
         }
         __syncthreads();
+        CBM_MARK(2);
 
         // ---- dPA_i[u,v] += sum_c dQ ----
         for (int uv = tid; uv < UV; uv += CBM_THREADS) {
@@ -656,6 +664,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                 }
             }
         }
+        CBM_MARK(3);
         // ---- dD[r,uv] = sum_c W4[c,r] dQ[c,uv];  dS = alpha dD (1 - D^2) overwrites the tanh table ----
         // ---- dx1[r,u] += sum_v dS[r,u,v];  dx2[r,v] -= sum_u dS[r,u,v] ----
         const int MT = Rp / 16;
@@ -692,6 +701,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                 }
             }
             __syncthreads();
+            CBM_MARK(4);
             if (V % 4 == 0) {
                 // 16-byte shared-memory loads: a dx1 task sums one row of V values, a dx2 task four adjacent columns
                 constexpr int QU = V / 4;
@@ -729,8 +739,13 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                 }
             }
             if (LEAN) __syncthreads();
+            CBM_MARK(5);
         }
     }
+    if (g_cbm_dbg && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 300))
+        printf("ctrgc_bwd_mma tid %d: table %lld  Q %lld  channel loop %lld  dPA+raw %lld  dD/dS %lld  dx1/dx2 %lld\n", tid, tph[0], tph[1],
+               tph[2], tph[3], tph[4], tph[5]);
+#undef CBM_MARK
     float dv[1] = {dalpha_acc};
     block_sum<1>(dv, red);
     if (tid == 0) atomicAdd(dalpha, dv[0]);
@@ -1119,7 +1134,14 @@ static int launch_bwd_mma(const CtrgcP& g0, int V, const Opnd& go, const void* x
                           float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha, cudaStream_t st) {
     CtrgcP g = g0;
     g.CT = CBM_CT;
-    static const int lean_env = [] { const char* e = getenv("TAMGCN_CBM_LEAN"); return e ? atoi(e) : 0; }();   // 1: force
+    static const int lean_env = [] { const char* e = getenv("TAMGCN_CBM_LEAN"); return e ? atoi(e) : 0; }();
+    static const int dbg_env = [] {
+        const char* e = getenv("TAMGCN_CBM_DBG");
+        const int v = e ? atoi(e) : 0;
+        if (v) cudaMemcpyToSymbol(g_cbm_dbg, &v, sizeof(int));
+        return v;
+    }();
+    (void)dbg_env;   // 1: force
     bool lean = lean_env == 1 && g.R > 16;
     size_t sm = ctrgc_bwd_mma_smem(V, g.R, lean);
     if (sm > 227 * 1024 && g.R > 16) { lean = true; sm = ctrgc_bwd_mma_smem(V, g.R, true); }
