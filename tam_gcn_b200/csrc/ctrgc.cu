@@ -388,7 +388,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 //   dD[r,uv]   = sum_c W4[c,r] dQ[c,uv]         -> dS = alpha dD (1 - D^2) -> dx1, dx2
 // LEAN (large R: the full tables do not fit 227 KB): the fp32 tanh table is not kept — the last phase recomputes
 // tanh from x1/x2 (same instruction, same value) and stages dS for 16 rows of r at a time.
-__device__ int g_cbm_dbg = 0;        // TAMGCN_CBM_DBG=1: block (0,0) prints its cycles per phase
+__device__ int g_cbm_dbg = 0;        // build with -DTAMGCN_CBM_PHASES, run with TAMGCN_CBM_DBG=1: block (0,0) prints its cycles per phase
 
 template <int V, bool LEAN>
 __global__ void __launch_bounds__(CBM_THREADS)
@@ -428,8 +428,12 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
     __syncthreads();
     for (int idx = tid; idx < UV; idx += CBM_THREADS) Db[R * UP + idx] = one;
     float dalpha_acc = 0.f;
+#ifdef TAMGCN_CBM_PHASES
     long long tph[6] = {0, 0, 0, 0, 0, 0}, tmark = clock64();
 #define CBM_MARK(ix) do { if (g_cbm_dbg) { const long long t_ = clock64(); tph[ix] += t_ - tmark; tmark = t_; } } while (0)
+#else
+#define CBM_MARK(ix) do { } while (0)
+#endif
 
     for (int i = 0; i < K; ++i) {
         __syncthreads();
@@ -742,9 +746,11 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
             CBM_MARK(5);
         }
     }
+#ifdef TAMGCN_CBM_PHASES
     if (g_cbm_dbg && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 300))
         printf("ctrgc_bwd_mma tid %d: table %lld  Q %lld  channel loop %lld  dPA+raw %lld  dD/dS %lld  dx1/dx2 %lld\n", tid, tph[0], tph[1],
                tph[2], tph[3], tph[4], tph[5]);
+#endif
 #undef CBM_MARK
     float dv[1] = {dalpha_acc};
     block_sum<1>(dv, red);
