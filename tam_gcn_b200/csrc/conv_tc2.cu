@@ -20,6 +20,7 @@
 // Persistent warp-specialised CTA, one per SM: warps 0-7 epilogue, warp 8 MMA issue, warps 9-16 producers.
 #include "tc_common.cuh"
 #include "tconv9_pack.cuh"
+#include <cuda.h>
 #include <cstdlib>
 
 namespace tamgcn {
@@ -63,7 +64,19 @@ struct C2P {
     uint32_t x_bytes, q_bytes, stage_bytes, off_hdr, off_coef, off_stg;
     long long ons;
     int dbg;                 // TAMGCN_C2_DBG (profiling aid): 8 = print per-role blocked cycles of block 0
+    int use_tma;             // plain 1x1 operand on 16-byte aligned planes: tiles fetched by cp.async.bulk.tensor (TMA)
 };
+
+// a CUtensorMap, passed by value as a __grid_constant__ kernel parameter
+struct alignas(64) C2TensorMap { unsigned long long v[16]; };
+
+// one 3-D box (64 positions x 64 channels x 1 sample) of the activation tensor -> shared memory (SWIZZLE_128B: the image
+// of the MN-major operand tile, c2_xoff), completion on `bar`
+__device__ __forceinline__ void c2_tma_load(uint32_t dst, const C2TensorMap* tm, int pos, int ch, int n, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(pos), "r"(ch), "r"(n), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 struct C2Hdr {
     uint64_t full[C2_SMAX], empty[C2_SMAX], tfull[2], tempty[2];
@@ -185,7 +198,8 @@ __device__ __forceinline__ void c2_xform_inplace(uint32_t dst, uint32_t dstq, bo
 
 template <int MODE, int PLAIN, int EXTRA>
 __global__ void __launch_bounds__(EXTRA ? C2_THREADS_SMALL : C2_THREADS_BIG, 1)
-conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restrict__ out, C2Epi ep) {
+conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restrict__ out, C2Epi ep,
+                const __grid_constant__ C2TensorMap tmap) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     C2Hdr* hdr = (C2Hdr*)(smem + p.off_hdr);
@@ -437,7 +451,15 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                     bulk_g2s(sx + p.x_bytes + p.q_bytes, wpack + ((size_t)kc * OCpad + (size_t)mt0 * 128) * 128, w_bytes, &hdr->full[stg]);
                 }
                 const int kbase = kc * 64, rows = min(64, p.KTp - kbase);
-                if (gran >= 4) {
+                if (PLAIN && p.use_tma) {
+                    // TMA: one thread asks for the nblk boxes of the stage; the barrier counts their bytes.  Rows / positions
+                    // outside the tensor arrive as zeros.
+                    if (pt == 0) {
+                        mbar_expect_tx(&hdr->full[stg], (uint32_t)p.nblk * 8192u);
+                        for (int b = 0; b < p.nblk; ++b) c2_tma_load(sx + (uint32_t)b * 8192u, &tmap, pos0 + 64 * b, kbase, n, &hdr->full[stg]);
+                    }
+                    mbar_arrive(&hdr->full[stg]);
+                } else if (gran >= 4) {
                     const unsigned tot = (unsigned)(rows * upr);
 #pragma unroll 1
                     for (unsigned idx = pt; idx < tot; idx += C2_PR_T) {
@@ -541,7 +563,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                 if (++stg == S) { stg = 0; ph ^= 1; }
             }
         }
-        if (gran >= 4) {
+        if (gran >= 4 && !(PLAIN && p.use_tma)) {
             c2_wait_group<0>();
             int newest = stg - 1; if (newest < 0) newest += S;
             for (int b = min(lag, cnt); b >= 1; --b) retire(b - 1, newest);
@@ -651,6 +673,42 @@ int conv_pack_weights(const float* W, int Cout, int Cin, int k, void* wf, void* 
     return check_launch("conv_pack_weights");
 }
 
+static bool c2_tma_enabled() {
+    static const bool on = [] { const char* e = getenv("TAMGCN_C2_TMA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*c2_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static c2_encode_fn c2_encoder() {
+    static c2_encode_fn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<c2_encode_fn>(f);
+    }();
+    return fn;
+}
+static bool c2_encode_tmap(C2TensorMap* out, const void* base, unsigned long long L, unsigned long long Cn, unsigned long long N,
+                           unsigned long long cstride_bytes, unsigned long long nstride_bytes) {
+    static_assert(sizeof(C2TensorMap) == sizeof(CUtensorMap), "tensor map size");
+    c2_encode_fn enc = c2_encoder();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (cstride_bytes & 15) || (nstride_bytes & 15)) return false;
+    if (N == 1) nstride_bytes = cstride_bytes * Cn;           // any multiple of 16 bytes: the dimension has one element
+    const cuuint64_t dims[3] = {L, Cn, N};
+    const cuuint64_t strides[2] = {cstride_bytes, nstride_bytes};
+    const cuuint32_t box[3] = {64, 64, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 template <int MODE>
 static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, void* out, long long ons, const C2Epi& ep,
                            cudaStream_t st) {
@@ -758,11 +816,21 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
         static const double epi4 = [] { const char* e = getenv("TAMGCN_C2_EPI4"); return e ? atof(e) : 2.5; }();
         if (epi4 > 0 && prod_work > epi4 * epi_work) p.n_epi = 4;
     }
+    // TMA for the plain 1x1 operand: a 3-D tensor map (positions, channels, samples) whose 64 x 64 boxes land as the
+    // SWIZZLE_128B tile the MMA reads.  Needs 16-byte aligned planes (global strides are multiples of 16 bytes).
+    C2TensorMap tmap = {};
+    p.use_tma = 0;
+    if (plain && p.fast && p.gran == 8 && c2_tma_enabled()) {
+        const int IC = p.IC;
+        if (c2_encode_tmap(&tmap, xo.p, (unsigned long long)p.Lin, (unsigned long long)IC, (unsigned long long)g.N,
+                           (unsigned long long)p.Lin * 2ull, (unsigned long long)xo.pns * 2ull))
+            p.use_tma = 1;
+    }
 #define C2_LAUNCH(PL, EX)                                                                                              \
     do {                                                                                                               \
         static SmemLimit lim;                                                                                          \
         ensure_smem(conv_tc2_kernel<MODE, PL, EX>, lim, sm);                                                           \
-        conv_tc2_kernel<MODE, PL, EX><<<grid, EX ? C2_THREADS_SMALL : C2_THREADS_BIG, sm, st>>>(p, xo, (const uint8_t*)wpack, (bf16*)out, ep); \
+        conv_tc2_kernel<MODE, PL, EX><<<grid, EX ? C2_THREADS_SMALL : C2_THREADS_BIG, sm, st>>>(p, xo, (const uint8_t*)wpack, (bf16*)out, ep, tmap); \
     } while (0)
     if (MODE == 0 || !extra) { if (plain) C2_LAUNCH(1, 0); else C2_LAUNCH(0, 0); }
     else { if (plain) C2_LAUNCH(1, 1); else C2_LAUNCH(0, 1); }
