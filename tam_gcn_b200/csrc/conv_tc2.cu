@@ -80,6 +80,7 @@ __device__ __forceinline__ void c2_tma_load(uint32_t dst, const C2TensorMap* tm,
 
 struct C2Hdr {
     uint64_t full[C2_SMAX], empty[C2_SMAX], tfull[2], tempty[2];
+    uint64_t raw[C2_SMAX];       // TMA-landed, not yet transformed (lazy operand fetched by tensor loads)
     uint32_t tmem_base;
     volatile uint32_t error;
 };
@@ -218,7 +219,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
 
     if (warp == C2_MMA_W) tmem_alloc(&hdr->tmem_base, (uint32_t)p.tmem_cols);
     if (tid == 0) {
-        for (int i = 0; i < C2_SMAX; ++i) { mbar_init(&hdr->full[i], C2_PR_T); mbar_init(&hdr->empty[i], 1); }
+        for (int i = 0; i < C2_SMAX; ++i) { mbar_init(&hdr->full[i], C2_PR_T); mbar_init(&hdr->empty[i], 1); mbar_init(&hdr->raw[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&hdr->tfull[i], 1); mbar_init(&hdr->tempty[i], C2_EPI_T); }
         hdr->error = 0;
         fence_mbar_init();
@@ -419,8 +420,9 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
             return (long long)ic * Lin + off;
         };
         // retire the chunk issued `age` chunks ago: transform a lazy operand in place, publish to the MMA warp
-        auto retire = [&](int age, int newest) {
+        auto retire = [&](int age, int newest, int chunk) {
             int sp = newest - age; if (sp < 0) sp += S;
+            if (!PLAIN && p.use_tma == 2) c2_wait(hdr, &hdr->raw[sp], (uint32_t)((chunk / S) & 1));     // the boxes have landed
             if (!PLAIN) {
                 const int kbase = age == 0 ? kb0 : (age == 1 ? kb1 : kb2), pos0 = age == 0 ? ps0 : (age == 1 ? ps1 : ps2);
                 const uint32_t sx = s0 + (uint32_t)sp * p.stage_bytes;
@@ -460,7 +462,14 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                     }
                     mbar_arrive(&hdr->full[stg]);
                 } else if (gran >= 4) {
-                    const unsigned tot = (unsigned)(rows * upr);
+                    const unsigned tot = (p.use_tma == 2) ? 0u : (unsigned)(rows * upr);
+                    if (p.use_tma == 2 && pt == 0) {
+                        // lazy one-tensor operand: the raw boxes arrive by TMA on their own barrier; the producers
+                        // transform them in place once landed (retire) and only then publish the stage
+                        mbar_expect_tx(&hdr->raw[stg], (uint32_t)p.nblk * 8192u);
+                        for (int b = 0; b < p.nblk; ++b) c2_tma_load(sx + (uint32_t)b * 8192u, &tmap, pos0 + 64 * b, kbase, n, &hdr->raw[stg]);
+                        mbar_arrive(&hdr->raw[stg]);
+                    }
 #pragma unroll 1
                     for (unsigned idx = pt; idx < tot; idx += C2_PR_T) {
                         const unsigned r = __umulhi(idx, umagic), pu = (idx - r * upr) * gran;
@@ -482,7 +491,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
                     ps2 = ps1; ps1 = ps0; ps0 = pos0;
                     if (cnt >= lag) {
                         if (lag == 2) c2_wait_group<2>(); else if (lag == 1) c2_wait_group<1>(); else c2_wait_group<0>();
-                        retire(lag, stg);
+                        retire(lag, stg, cnt - lag);
                     }
                 } else if (p.ra8) {
                     // stride-1 taps whose V-row shift is not 8-byte aligned (V = 25: 50-byte rows): 8 consecutive positions of
@@ -566,7 +575,7 @@ conv_tc2_kernel(C2P p, Opnd xo, const uint8_t* __restrict__ wpack, bf16* __restr
         if (gran >= 4 && !(PLAIN && p.use_tma)) {
             c2_wait_group<0>();
             int newest = stg - 1; if (newest < 0) newest += S;
-            for (int b = min(lag, cnt); b >= 1; --b) retire(b - 1, newest);
+            for (int b = min(lag, cnt); b >= 1; --b) retire(b - 1, newest, cnt - b);
         }
     }
     if ((p.dbg & 8) && blockIdx.x == 0 && (tid == 0 || tid == 256 || tid == C2_MMA_W * 32 || tid == C2_PR_T0))
@@ -820,11 +829,13 @@ static int launch_conv_tc2(const ConvP& g, const Opnd& xo, const void* wpack, vo
     // SWIZZLE_128B tile the MMA reads.  Needs 16-byte aligned planes (global strides are multiples of 16 bytes).
     C2TensorMap tmap = {};
     p.use_tma = 0;
-    if (plain && p.fast && p.gran == 8 && c2_tma_enabled()) {
+    // (lazy one-tensor operands through TMA + in-place transform: parity-green, no measurable gain -> opt-in)
+    static const int tma_lazy = [] { const char* e = getenv("TAMGCN_C2_TMA_LAZY"); return e ? atoi(e) : 0; }();
+    if ((plain || (!xo.q && tma_lazy)) && p.fast && p.gran == 8 && c2_tma_enabled()) {
         const int IC = p.IC;
         if (c2_encode_tmap(&tmap, xo.p, (unsigned long long)p.Lin, (unsigned long long)IC, (unsigned long long)g.N,
                            (unsigned long long)p.Lin * 2ull, (unsigned long long)xo.pns * 2ull))
-            p.use_tma = 1;
+            p.use_tma = plain ? 1 : 2;       // 2: raw boxes, transformed in place by the producers
     }
 #define C2_LAUNCH(PL, EX)                                                                                              \
     do {                                                                                                               \
