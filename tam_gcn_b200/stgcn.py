@@ -58,7 +58,13 @@ class st_gcn(nn.Module):
     def forward(self, x, A):
         assert A.size(0) == self.gcn.kernel_size
         if self.dropout_p and self.training:
-            raise NotImplementedError('st_gcn: dropout > 0 in training mode is not fused yet (reference default is 0)')
+            # Rare path (the reference's own configs use dropout 0 here, models/stgcn.py:81): the graph convolution runs on
+            # the native kernels; the TCN tail, whose dropout mask sits between BatchNorm and the residual sum, goes
+            # through the same torch modules on the GPU (cuDNN), under autocast when activations are bf16.
+            g, _ = self.gcn(x, A)
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(g.dtype == torch.bfloat16)):
+                out = self.relu(self.tcn(g) + self.residual(x))
+            return out.to(g.dtype), A
         return Fn.StGcnFn.apply(x, A, self, *Fn.st_gcn_params(self)), A
 
 

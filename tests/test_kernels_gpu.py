@@ -76,7 +76,9 @@ CONV_GEOMS = [  # (Cin, Cout, T, k, s, d)
     # ... and the stride-2 layers (l5, l8)
     (64, 64, 40, 9, 2, 1), (128, 128, 75, 9, 2, 1), (64, 128, 31, 9, 2, 1),
     # 1x1 graph convolutions on planes of odd length (T*V % 4 != 0 at V = 25): weight gradient through tconv9's k = 1 tiles
-    (64, 192, 75, 1, 1, 1), (256, 96, 30, 1, 1, 1)]
+    (64, 192, 75, 1, 1, 1), (256, 96, 30, 1, 1, 1),
+    # ragged channel counts / odd lengths through the same kernels
+    (80, 96, 23, 9, 1, 1), (64, 64, 41, 9, 2, 1), (96, 80, 33, 7, 1, 1)]
 
 
 def _pad(k, d):

@@ -187,6 +187,44 @@ def test_input_gradient_in_eval_mode_stgcn():
     assert O.rel_err(sal, sal_ref) < 5e-3
 
 
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+def test_st_gcn_dropout_training_path(dt):
+    """st_gcn(dropout > 0) in training mode (models/stgcn.py:81): the mask sits between BatchNorm and the residual sum.
+    Checked against the same modules composed in torch with the same RNG state, and for gradient flow; in eval mode the
+    block must equal the dropout-free one."""
+    _cuda()
+    import tam_gcn_b200
+    from tam_gcn_b200 import stgcn as S
+    tam_gcn_b200.set_act_dtype(dt)
+    try:
+        torch.manual_seed(0)
+        blk = S.st_gcn(16, 32, (9, 3), stride=2, dropout=0.4).cuda()
+        ref = S.st_gcn(16, 32, (9, 3), stride=2, dropout=0).cuda()
+        ref.load_state_dict(blk.state_dict())
+        x = torch.randn(3, 16, 20, 25, device='cuda').to(dt)
+        A = torch.rand(3, 25, 25, device='cuda') * 0.2
+        blk.eval(); ref.eval()
+        ye, _ = blk(x, A)
+        yr, _ = ref(x, A)
+        assert torch.equal(ye, yr)
+        blk.train()
+        xg = x.clone().requires_grad_(True)
+        torch.manual_seed(7)
+        y, _ = blk(xg, A)
+        assert y.shape == (3, 32, 10, 25) and y.dtype == dt and torch.isfinite(y.float()).all()
+        y.float().sum().backward()
+        assert torch.isfinite(xg.grad.float()).all() and float(xg.grad.float().abs().sum()) > 0
+        for n_, p_ in blk.named_parameters():
+            assert p_.grad is not None and torch.isfinite(p_.grad).all(), n_
+        # the dropout really drops: an undropped evaluation of the same (training-mode) block differs
+        blk.tcn[4].p = 0.0
+        y0, _ = blk(x, A)
+        blk.tcn[4].p = 0.4
+        assert float((y.detach().float() - y0.detach().float()).abs().max()) > 1e-3
+    finally:
+        tam_gcn_b200.set_act_dtype(torch.float32)
+
+
 def test_three_dim_input_and_python_alpha():
     _cuda()
     import tam_gcn_b200.ctrgcn as C
