@@ -530,8 +530,14 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
 #pragma unroll
                 for (int nt = 0; nt < NTn; ++nt) dq[mu][nt][0] = dq[mu][nt][1] = dq[mu][nt][2] = dq[mu][nt][3] = 0.f;
 
-            const bool fastld = (V % 2 == 0) && ((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(xp) |
-                                                  (gq ? reinterpret_cast<uintptr_t>(gq) : 0)) & 3) == 0;
+            // 4-byte aligned planes: every fragment word is one aligned 32-bit load (even V), or — odd V with an even number
+            // of rows, where odd rows start 2 bytes into a word — two aligned loads and a funnel shift whose amount is a
+            // per-lane constant (row parity = parity of gid); the last row is odd, so no word reaches past the plane
+            const bool al4 = ((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(xp) |
+                               (gq ? reinterpret_cast<uintptr_t>(gq) : 0)) & 3) == 0;
+            const bool oddld = (V % 2 == 1) && al4 && (Tn % 2 == 0);
+            const bool fastld = ((V % 2 == 0) && al4) || oddld;
+            const int odd = oddld ? (gid & 1) : 0, fsh = odd * 16;
             for (int t0 = 0; t0 < Tn; t0 += 16) {
                 uint32_t ga[2][4];                       // cotangent, [row half][u block], lazy operand applied
                 uint32_t xa[2][NTn];                     // x3 rows, [row half][v block]
@@ -546,13 +552,27 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                         const long long ro = (long long)t * V + 2 * tig;
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
-                            const bool ok = tok && 8 * b + 2 * tig < V;
-                            pw[h][b] = ok ? __ldg(reinterpret_cast<const unsigned*>(gp + ro + 8 * b)) : 0u;
-                            qw[h][b] = (ok && gq) ? __ldg(reinterpret_cast<const unsigned*>(gq + ro + 8 * b)) : 0u;
+                            const bool ok = tok && 8 * b + 2 * tig < V, ok1 = odd && 8 * b + 2 * tig + 1 < V;   // second word: only if its element is real
+                            const unsigned* wp = reinterpret_cast<const unsigned*>(gp + ro + 8 * b - odd);
+                            const unsigned w0 = ok ? __ldg(wp) : 0u, w1 = (ok && ok1) ? __ldg(wp + 1) : 0u;
+                            pw[h][b] = (V % 2) ? __funnelshift_r(w0, w1, fsh) : w0;
+                            if (gq) {
+                                const unsigned* wq = reinterpret_cast<const unsigned*>(gq + ro + 8 * b - odd);
+                                const unsigned q0 = ok ? __ldg(wq) : 0u, q1 = (ok && ok1) ? __ldg(wq + 1) : 0u;
+                                qw[h][b] = (V % 2) ? __funnelshift_r(q0, q1, fsh) : q0;
+                            } else {
+                                qw[h][b] = 0u;
+                            }
                         }
 #pragma unroll
-                        for (int b = 0; b < NTn; ++b)
-                            xa[h][b] = (tok && 8 * b + 2 * tig < V) ? __ldg(reinterpret_cast<const unsigned*>(xp + ro + 8 * b)) : 0u;
+                        for (int b = 0; b < NTn; ++b) {
+                            const bool ok = tok && 8 * b + 2 * tig < V, ok1 = odd && 8 * b + 2 * tig + 1 < V;
+                            const unsigned* wx = reinterpret_cast<const unsigned*>(xp + ro + 8 * b - odd);
+                            const unsigned x0 = ok ? __ldg(wx) : 0u, x1 = (ok && ok1) ? __ldg(wx + 1) : 0u;
+                            unsigned xw = (V % 2) ? __funnelshift_r(x0, x1, fsh) : x0;
+                            if ((V % 2) && 8 * b + 2 * tig + 1 >= V) xw &= 0xffffu;
+                            xa[h][b] = xw;
+                        }
                     }
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
@@ -565,6 +585,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                                 hi = fmaf(cf.b, __uint_as_float(qw[h][b] & 0xffff0000u), hi);
                             }
                             if (go.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                            if ((V % 2) && 8 * b + 2 * tig + 1 >= V) hi = 0.f;
                             ga[h][b] = ok ? pack2_bf16(lo, hi) : 0u;
                         }
                 } else {
