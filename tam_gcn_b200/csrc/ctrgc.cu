@@ -390,13 +390,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // tanh from x1/x2 (same instruction, same value) and stages dS for 16 rows of r at a time.
 __device__ int g_cbm_dbg = 0;        // build with -DTAMGCN_CBM_PHASES, run with TAMGCN_CBM_DBG=1: block (0,0) prints its cycles per phase
 
-template <int V, bool LEAN>
-__global__ void __launch_bounds__(CBM_THREADS)
+// CT channels per CTA, one warp each: 16 (512 threads) or 8 (256 threads: half the shared memory and registers per
+// CTA, so two or three CTAs share an SM and one CTA's barrier / load latencies hide behind the others' work)
+template <int V, bool LEAN, int CT>
+__global__ void __launch_bounds__(CT * 32, CT == 8 ? 2 : 1)
 ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float* __restrict__ x1,
                      const float* __restrict__ x2, const float* __restrict__ W4, const float* __restrict__ b4,
                      const float* __restrict__ PA, const float* __restrict__ alpha_p, bf16* __restrict__ dx3,
                      long long dx3ns, float* dx1, float* dx2, float* dW4, float* db4, float* dPA, float* dalpha) {
-    constexpr int CT = CBM_CT;
+    constexpr int THR = CT * 32;
     constexpr int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8;      // uv = u*V + v; bf16 row pitch (conflict-free)
     constexpr int NTn = (V + 7) / 8;          // 8-wide v tiles (20 -> 3, 25 -> 4)
     constexpr int QP = 40;                    // pitch (bf16) of a Qt row: 32 u + 8 padding
@@ -422,11 +424,11 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
     const long long TV = (long long)Tn * V;
     const bf16 zero = __float2bfloat16_rn(0.f), one = __float2bfloat16_rn(1.f);
 
-    for (int idx = tid; idx < CT * 8 * NTn * QP; idx += CBM_THREADS) Qt[idx] = zero;
+    for (int idx = tid; idx < CT * 8 * NTn * QP; idx += THR) Qt[idx] = zero;
     // Db: zero everywhere (16-byte stores; DR * UP * 2 bytes is a multiple of 16), then the ones row
-    for (int idx = tid; idx < DR * UP / 8; idx += CBM_THREADS) reinterpret_cast<uint4*>(Db)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    for (int idx = tid; idx < DR * UP / 8; idx += THR) reinterpret_cast<uint4*>(Db)[idx] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (int idx = tid; idx < UV; idx += CBM_THREADS) Db[R * UP + idx] = one;
+    for (int idx = tid; idx < UV; idx += THR) Db[R * UP + idx] = one;
     float dalpha_acc = 0.f;
 #ifdef TAMGCN_CBM_PHASES
     long long tph[6] = {0, 0, 0, 0, 0, 0}, tmark = clock64();
@@ -438,25 +440,25 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
     for (int i = 0; i < K; ++i) {
         __syncthreads();
         // ---- parameters of this subset and the tanh table ----
-        for (int idx = tid; idx < R * V; idx += CBM_THREADS) {
+        for (int idx = tid; idx < R * V; idx += THR) {
             x12s[idx] = __ldg(x1 + (long long)n * g.x12ns + i * R * V + idx);
             x12s[R * V + idx] = __ldg(x2 + (long long)n * g.x12ns + i * R * V + idx);
         }
-        for (int idx = tid; idx < 16 * RW; idx += CBM_THREADS) {
+        for (int idx = tid; idx < 16 * RW; idx += THR) {
             const int c = idx / RW, r = idx - c * RW;
             W4b[idx] = (c < nc && r < R) ? __float2bfloat16_rn(__ldg(W4 + ((long long)i * g.Cout + c0 + c) * R + r)) : zero;
         }
-        for (int idx = tid; idx < Rp * 24; idx += CBM_THREADS) {
+        for (int idx = tid; idx < Rp * 24; idx += THR) {
             const int r = idx / 24, c = idx - r * 24;
             W4T[idx] = (c < nc && r < R) ? __float2bfloat16_rn(__ldg(W4 + ((long long)i * g.Cout + c0 + c) * R + r)) : zero;
         }
-        for (int idx = tid; idx < CT; idx += CBM_THREADS) b4s[idx] = idx < nc ? __ldg(b4 + i * g.Cout + c0 + idx) : 0.f;
-        for (int idx = tid; idx < 16 * UP; idx += CBM_THREADS) dQc[idx] = zero;
+        for (int idx = tid; idx < CT; idx += THR) b4s[idx] = idx < nc ? __ldg(b4 + i * g.Cout + c0 + idx) : 0.f;
+        for (int idx = tid; idx < 16 * UP; idx += THR) dQc[idx] = zero;
         __syncthreads();
         if (V % 4 == 0) {
             // four consecutive v of one (r, u) per step: one x1 value, one 16-byte x2 load, vector stores
             constexpr int QR = UVp / 4, QU = V / 4;
-            for (int idx = tid; idx < R * QR; idx += CBM_THREADS) {
+            for (int idx = tid; idx < R * QR; idx += THR) {
                 const int r = idx / QR, q = idx - r * QR, u = q / QU, v = 4 * (q - u * QU);
                 const float a = x12s[r * V + u];
                 const float4 b = *reinterpret_cast<const float4*>(x12s + R * V + r * V + v);
@@ -465,7 +467,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                 *reinterpret_cast<uint2*>(Db + (size_t)r * UP + 4 * q) = make_uint2(pack2_bf16(d.x, d.y), pack2_bf16(d.z, d.w));
             }
         } else {
-            for (int idx = tid; idx < R * UVp; idx += CBM_THREADS) {
+            for (int idx = tid; idx < R * UVp; idx += THR) {
                 const int r = idx / UVp, uv = idx - r * UVp;
                 float d = 0.f;
                 if (uv < UV) {
@@ -479,7 +481,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
         __syncthreads();
         CBM_MARK(0);
         // ---- Q = alpha (W4 . D + b4) + PA, as Qt[c][v][u] (bf16) ----
-        for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
+        for (int nt = warp; nt < UVp / 8; nt += THR / 32) {
             float d[4] = {0.f, 0.f, 0.f, 0.f};
             // PA[i][uv], PA[i][uv+1] of this lane's accumulator columns: requested before the MMAs so that the global
             // load latency is hidden behind them (it used to stall the scatter below: 10 % of the kernel's samples)
@@ -662,7 +664,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
         CBM_MARK(2);
 
         // ---- dPA_i[u,v] += sum_c dQ ----
-        for (int uv = tid; uv < UV; uv += CBM_THREADS) {
+        for (int uv = tid; uv < UV; uv += THR) {
             float s = 0.f;
             for (int c = 0; c < nc; ++c) s += dQs[c * UV + uv];
             atomicAdd(dPA + i * UV + uv, s);
@@ -696,7 +698,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
         for (int pass = 0; pass < (LEAN ? MT : 1); ++pass) {
             const int mt_lo = LEAN ? pass : 0, mt_hi = LEAN ? pass + 1 : MT;
             const int r_lo = mt_lo * 16, r_n = min(R, mt_hi * 16) - r_lo;       // rows staged in Df this pass
-            for (int nt = warp; nt < UVp / 8; nt += CBM_THREADS / 32) {
+            for (int nt = warp; nt < UVp / 8; nt += THR / 32) {
                 uint32_t b0, b1;
                 ldsm_x2_trans(b0, b1, dQc + (size_t)(lane & 15) * UP + nt * 8);
                 const int uv = nt * 8 + 2 * tig;
@@ -730,7 +732,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
             if (V % 4 == 0) {
                 // 16-byte shared-memory loads: a dx1 task sums one row of V values, a dx2 task four adjacent columns
                 constexpr int QU = V / 4;
-                for (int task = tid; task < r_n * V; task += CBM_THREADS) {
+                for (int task = tid; task < r_n * V; task += THR) {
                     const int rl = task / V, u = task - rl * V, r = r_lo + rl;
                     const float4* ds = reinterpret_cast<const float4*>(Df + (size_t)rl * UVp + u * V);
                     float s = 0.f;
@@ -738,7 +740,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                     for (int o = 0; o < QU; ++o) { const float4 d = ds[o]; s += (d.x + d.y) + (d.z + d.w); }
                     atomicAdd(dx1 + (long long)n * g.x12ns + (i * R + r) * V + u, s);
                 }
-                for (int task = tid; task < r_n * QU; task += CBM_THREADS) {
+                for (int task = tid; task < r_n * QU; task += THR) {
                     const int rl = task / QU, vq = task - rl * QU, r = r_lo + rl;
                     const float* ds = Df + (size_t)rl * UVp + 4 * vq;
                     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -751,7 +753,7 @@ ctrgc_bwd_mma_kernel(CtrgcP g, Opnd go, const bf16* __restrict__ x3, const float
                     atomicAdd(dst, -s.x); atomicAdd(dst + 1, -s.y); atomicAdd(dst + 2, -s.z); atomicAdd(dst + 3, -s.w);
                 }
             } else {
-                for (int task = tid; task < 2 * r_n * V; task += CBM_THREADS) {
+                for (int task = tid; task < 2 * r_n * V; task += THR) {
                     const int which = task / (r_n * V), rem = task - which * r_n * V, rl = rem / V, w = rem - rl * V;
                     const int r = r_lo + rl;
                     const float* ds = Df + (size_t)rl * UVp + (which ? w : w * V);
@@ -1148,11 +1150,11 @@ static int launch_fwd(const CtrgcP& g, int V, const void* x3, const float* x1, c
     return check_launch("ctrgc_fwd");
 }
 
-static size_t ctrgc_bwd_mma_smem(int V, int R, bool lean) {
+static size_t ctrgc_bwd_mma_smem(int V, int R, bool lean, int CT = CBM_CT) {
     const int UV = V * V, UVp = (UV + 15) & ~15, UP = UVp + 8, NTn = (V + 7) / 8;
     const int Rp = (R + 15) & ~15, RW = Rp + 8, NRt = (R + 1 + 7) / 8, DR = NRt * 8 > Rp ? NRt * 8 : Rp;
-    return sizeof(float) * ((size_t)(lean ? 16 : R) * UVp + (size_t)CBM_CT * UV + CBM_CT + 2 * (size_t)R * V + 64) +
-           sizeof(bf16) * ((size_t)DR * UP + 16 * (size_t)UP + 16 * RW + (size_t)Rp * 24 + (size_t)CBM_CT * 8 * NTn * 40) + 16;
+    return sizeof(float) * ((size_t)(lean ? 16 : R) * UVp + (size_t)CT * UV + CT + 2 * (size_t)R * V + 64) +
+           sizeof(bf16) * ((size_t)DR * UP + 16 * (size_t)UP + 16 * RW + (size_t)Rp * 24 + (size_t)CT * 8 * NTn * 40) + 16;
 }
 
 // returns 1 if launched, 0 if the shape does not fit (caller falls back to the SIMT kernel), <0 on error
@@ -1173,16 +1175,22 @@ static int launch_bwd_mma(const CtrgcP& g0, int V, const Opnd& go, const void* x
     size_t sm = ctrgc_bwd_mma_smem(V, g.R, lean);
     if (sm > 227 * 1024 && g.R > 16) { lean = true; sm = ctrgc_bwd_mma_smem(V, g.R, true); }
     if (sm > 227 * 1024 || g.R > 128 || (g.R & 1)) return 0;
+    // 8-channel CTAs, two per SM: measured slower than one 16-channel CTA (2.23 vs 2.13 ms at N'=2048; the tables are
+    // rebuilt twice as often) -> opt-in, TAMGCN_CBM_CT=8
+    static const int ct_env = [] { const char* e = getenv("TAMGCN_CBM_CT"); return e ? atoi(e) : 0; }();
+    const size_t sm8 = ctrgc_bwd_mma_smem(V, g.R, lean, 8);
+    const bool ct8 = ct_env == 8 && !lean && g.R <= 55 && 2 * (sm8 + 1024) <= 227 * 1024;
+    if (ct8) { g.CT = 8; sm = sm8; }
     dim3 grid(cdiv(g.Cout, g.CT), g.N);
-#define CBM_LAUNCH(VV, LL)                                                                                                  \
+#define CBM_LAUNCH(VV, LL, CC)                                                                                              \
     do {                                                                                                                    \
         static SmemLimit lim;                                                                                               \
-        ensure_smem(ctrgc_bwd_mma_kernel<VV, LL>, lim, sm);                                                                 \
-        ctrgc_bwd_mma_kernel<VV, LL><<<grid, CBM_THREADS, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha,       \
+        ensure_smem(ctrgc_bwd_mma_kernel<VV, LL, CC>, lim, sm);                                                             \
+        ctrgc_bwd_mma_kernel<VV, LL, CC><<<grid, CC * 32, sm, st>>>(g, go, (const bf16*)x3, x1, x2, W4, b4, PA, alpha,      \
                                                                     (bf16*)dx3, dx3ns, dx1, dx2, dW4, db4, dPA, dalpha);   \
     } while (0)
-    if (V == 20) { if (lean) CBM_LAUNCH(20, true); else CBM_LAUNCH(20, false); }
-    else         { if (lean) CBM_LAUNCH(25, true); else CBM_LAUNCH(25, false); }
+    if (V == 20) { if (lean) CBM_LAUNCH(20, true, 16); else if (ct8) CBM_LAUNCH(20, false, 8); else CBM_LAUNCH(20, false, 16); }
+    else         { if (lean) CBM_LAUNCH(25, true, 16); else if (ct8) CBM_LAUNCH(25, false, 8); else CBM_LAUNCH(25, false, 16); }
 #undef CBM_LAUNCH
     count_launch();
     const int rc = check_launch("ctrgc_bwd(mma)");
