@@ -20,6 +20,8 @@ Host-side runtime pieces (all per Trainer, nothing global):
     slice is launched from inside backward as soon as their gradients are final and overlaps the lower layers'
     backward; the 1/world_size factor is folded into the optimiser kernel.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -47,11 +49,15 @@ class Trainer:
         self.arena = _arena.ZeroArena(self.device)
         self.packs = ops.PackCache(model) if self.cuda else None
         self._arena_keep = []                       # buffers baked into captured graphs: never freed
-        self.side = torch.cuda.Stream(device=self.device) if (self.cuda and side_stream) else None
-        import os
-        self.wgrad_sm_share = int(wgrad_sm_share or os.environ.get('TAMGCN_WGRAD_SM_SHARE', 50))
+        # stream priorities (TAMGCN_STREAM_PRIO=0 turns them off): the step graph is captured on a high-priority stream (the data-gradient
+        # chain), the weight gradients run at low priority, so a freed SM goes to the critical path first
+        self.prio = os.environ.get('TAMGCN_STREAM_PRIO', '1') == '1'
+        hi = -1 if self.prio else 0
+        self.side = torch.cuda.Stream(device=self.device, priority=0) if (self.cuda and side_stream) else None
+        self.wgrad_sm_share = int(wgrad_sm_share or os.environ.get('TAMGCN_WGRAD_SM_SHARE', 75))
         self.bwd_main_sm_share = int(os.environ.get('TAMGCN_BWD_MAIN_SM_SHARE', 100)) if self.side is not None else 100
-        self.branch_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)] if (self.cuda and side_stream) else None
+        self.branch_streams = [torch.cuda.Stream(device=self.device, priority=hi) for _ in range(2)] if (self.cuda and side_stream) else None
+        self.capture_stream = torch.cuda.Stream(device=self.device, priority=hi) if (self.cuda and self.prio) else None
         self.overlap = bool(overlap_allreduce) and self.world > 1 and self.cuda
         self.graph = None
         self.static_x = self.static_y = self.static_loss = None
@@ -191,7 +197,7 @@ class Trainer:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _C.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self.capture_stream):
             self.static_loss = self._step_body(self.static_x, self.static_y)
         self.captured_launches = _C.launch_count() - n0
 
