@@ -454,6 +454,7 @@ tconv9_kernel(T9P p, Opnd x, const unsigned char* __restrict__ wpack, bf16* __re
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+    if (threadIdx.x == 0 && hdr->error) printf("tamgcn: tconv9 pipeline timeout in block %d\n", blockIdx.x);
 }
 
 // =====================================================================================================================
@@ -740,6 +741,7 @@ tconv9_wgrad_kernel(W9P p, Opnd dy, Opnd x, float* __restrict__ dW, float* __res
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
+    if (threadIdx.x == 0 && hdr->error) printf("tamgcn: tconv9 pipeline timeout in block %d\n", blockIdx.x);
 }
 
 static bool t9_disabled() {
