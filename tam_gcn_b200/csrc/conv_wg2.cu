@@ -476,7 +476,10 @@ int conv_wgrad_tc2(const tamgcn_conv_geom* gg, const Opnd& dy, const Opnd& x, fl
     p.off_coef = p.off_hdr + szH;
     const size_t sm = (size_t)p.off_coef + szC + 1024;
     const int gx = (g.Cout + 127) / 128, gy = (g.Cin + NT - 1) / NT;
-    long long Z = (long long)occ * wgrad_sms() / (gx * gy);
+    // TAMGCN_W2_ZMUL (experiment): more, shorter CTAs than SM slots, so that SMs return to the (higher-priority) data-gradient
+    // chain more often; costs split-K atomics and prologues
+    static const int zmul = [] { const char* e = getenv("TAMGCN_W2_ZMUL"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+    long long Z = (long long)zmul * occ * wgrad_sms() / (gx * gy);
     if (Z < 1) Z = 1;
     if (Z > units) Z = units;
     if (Z > 65535) Z = 65535;
