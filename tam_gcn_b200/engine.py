@@ -239,6 +239,11 @@ class Predictor:
         self.packs = ops.PackCache(model)
         self.use_graph = use_graph
         self.graph = None
+        # independent branches of a block (MS-TCN branches, the strided 1x1 next to the heads) on two extra streams inside
+        # the captured forward (TAMGCN_INFER_BRANCHES=0 turns it off)
+        dev = next(model.parameters()).device
+        self.branch_streams = ([torch.cuda.Stream(device=dev) for _ in range(2)]
+                               if (dev.type == 'cuda' and use_graph and os.environ.get('TAMGCN_INFER_BRANCHES', '1') == '1') else None)
         self.static_x = self.static_out = None
         self.captured_launches = 0
 
@@ -254,14 +259,14 @@ class Predictor:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    with Fn.pack_cache(self.packs):
+                    with Fn.pack_cache(self.packs), ops.branches(self.branch_streams):
                         self.model(self.static_x)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             n0 = _C.launch_count()
-            with torch.cuda.graph(self.graph), Fn.pack_cache(self.packs):     # one batched weight-tile refresh per replay
-                self.static_out = self.model(self.static_x)
+            with torch.cuda.graph(self.graph), Fn.pack_cache(self.packs), ops.branches(self.branch_streams):
+                self.static_out = self.model(self.static_x)           # one batched weight-tile refresh per replay
             self.captured_launches = _C.launch_count() - n0
         self.static_x.copy_(x, non_blocking=True)
         self.graph.replay()

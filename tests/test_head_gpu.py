@@ -247,3 +247,31 @@ def test_graph_replay_equals_eager_bf16():
         small = ta.step(x[:4], y[:4])                          # different shape: eager fallback, still a valid step
         assert torch.isfinite(small)
         assert ta.captured_launches > 100
+
+
+@pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
+def test_predictor_graph_equals_eager_forward(dt):
+    """engine.Predictor: the captured eval forward (batched weight pack, branch streams) == the plain module call,
+    on the device-resident and the from-host entry; a new batch shape re-captures."""
+    dev = _dev()
+    import tam_gcn_b200
+    from tam_gcn_b200 import engine
+    x = O.synthetic_skeletons(6, 52, 20, 1, C=3, seed=9).to(dev)
+    with tam_gcn_b200.act_dtype(dt):
+        m = _fresh_model().to(dev)
+        for _ in range(3):                                     # calibrate the running statistics
+            m.train()(x)
+        m.eval()
+        with torch.no_grad():
+            ref = m(x).float()
+        p = engine.Predictor(m)
+        out = p(x).float().clone()
+        assert rel(out, ref) < (1e-6 if dt == torch.float32 else 1e-2)
+        out2 = p(x).float().clone()                            # second call = pure replay
+        assert torch.equal(out, out2)
+        host = x.cpu().pin_memory()
+        assert torch.equal(p.from_host(host).float(), out.cpu())
+        small = p(x[:2]).float()                               # new shape: a new graph
+        with torch.no_grad():
+            assert rel(small, m(x[:2]).float()) < (1e-6 if dt == torch.float32 else 1e-2)
+        assert p.captured_launches > 50
