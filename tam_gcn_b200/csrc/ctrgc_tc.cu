@@ -736,6 +736,9 @@ int ctrgc_fwd_tc(const void* x3, long long x3ns, int N, int Cout, int T, int V, 
         const int rc4 = ctrgc_fwd_tc4(x3, x3ns, N, Cout, T, V, K, R, x1, x2, x12ns, W4, b4, PA, alpha, y, yns, ssum, ssq, st);
         if (rc4 != 0) return rc4;
     }
+    // TAMGCN_CTC_GENERIC=0: leave the shapes of this (older) kernel to the warp-MMA forward of ctrgc.cu
+    static const bool generic_off = [] { const char* e = getenv("TAMGCN_CTC_GENERIC"); return e && e[0] == '0'; }();
+    if (generic_off) return 0;
     if (V != 20 && V != 25) return 0;
     const int VS = V == 20 ? 20 : 32, VN = V == 20 ? 24 : 32, VP = V == 20 ? 20 : 28;
     if (K * VS > 128 || K > 8 || R > 64 || Cout > 2048) return 0;

@@ -56,7 +56,8 @@ class Trainer:
         self.side = torch.cuda.Stream(device=self.device, priority=0) if (self.cuda and side_stream) else None
         self.wgrad_sm_share = int(wgrad_sm_share or os.environ.get('TAMGCN_WGRAD_SM_SHARE', 75))
         self.bwd_main_sm_share = int(os.environ.get('TAMGCN_BWD_MAIN_SM_SHARE', 100)) if self.side is not None else 100
-        self.branch_streams = [torch.cuda.Stream(device=self.device, priority=hi) for _ in range(2)] if (self.cuda and side_stream) else None
+        nbr = int(os.environ.get('TAMGCN_BRANCH_STREAMS', 2))
+        self.branch_streams = [torch.cuda.Stream(device=self.device, priority=hi) for _ in range(nbr)] if (self.cuda and side_stream and nbr > 0) else None
         self.capture_stream = torch.cuda.Stream(device=self.device, priority=hi) if (self.cuda and self.prio) else None
         self.overlap = bool(overlap_allreduce) and self.world > 1 and self.cuda
         self.graph = None
