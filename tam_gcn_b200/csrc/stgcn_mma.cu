@@ -21,6 +21,7 @@
 namespace tamgcn {
 
 #define SG_WARPS 8
+#define SG_D 2                                   // input blocks in flight per warp (ring depth; 3 measured equal: the kernels are issue-bound)
 #define SG_THREADS (SG_WARPS * 32)
 
 struct SgP {
@@ -171,9 +172,9 @@ graph_agg_fwd_mma_kernel(SgP p, const bf16* __restrict__ y, const float* __restr
     constexpr int NTn = SgCfg<V>::NTn, SGB = SgCfg<V>::SGB;
     extern __shared__ __align__(16) unsigned char sg_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
-    unsigned char* my = sg_smem + (size_t)warp * (2 * K + 1) * SGB;          // [2][K] input blocks + 1 output block
+    unsigned char* my = sg_smem + (size_t)warp * (SG_D * K + 1) * SGB;       // [SG_D][K] input blocks + 1 output block
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
-    unsigned char* obuf = my + 2 * K * SGB;
+    unsigned char* obuf = my + SG_D * K * SGB;
     // B fragments: B[k = v][n = w] = A_k[v][w], pairs along v
     uint32_t bq[K][2][NTn][2];
 #pragma unroll
@@ -208,7 +209,7 @@ graph_agg_fwd_mma_kernel(SgP p, const bf16* __restrict__ y, const float* __restr
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const unsigned char* src = src_of(s_unit, s_tb, k);
-                const int o = ((int)(j & 1) * K + k) * SGB;
+                const int o = ((int)(j % SG_D) * K + k) * SGB;
                 sg_stage(my_s + o, my + o, src, rows * V * 2, ybeg, yend, lane);
             }
             if (++s_tb == p.nblk) { s_tb = 0; s_unit += wstride; }
@@ -216,12 +217,12 @@ graph_agg_fwd_mma_kernel(SgP p, const bf16* __restrict__ y, const float* __restr
         sg_commit();
     };
     (void)total;
-    stage(0);
+    for (int d = 0; d < SG_D - 1; ++d) stage(d);
     int unit = wg, tb = 0;
     float s1 = 0.f, s2 = 0.f;
     for (long long j = 0; j < J; ++j) {
-        stage(j + 1);
-        sg_wait<1>();
+        stage(j + SG_D - 1);
+        sg_wait<SG_D - 1>();
         __syncwarp();
         const int rows = min(16, p.T - tb * 16);
         const int n = unit / p.C, c = unit - n * p.C;
@@ -233,7 +234,7 @@ graph_agg_fwd_mma_kernel(SgP p, const bf16* __restrict__ y, const float* __restr
             const unsigned char* src = src_of(unit, tb, k);
             const int es = (int)(reinterpret_cast<uintptr_t>(src) & 15) >> 1;
             uint32_t xa[2][4];
-            sg_frags<V>(my + ((int)(j & 1) * K + k) * SGB, es + gid * V + 2 * tig, rows, gid, tig, xa);
+            sg_frags<V>(my + ((int)(j % SG_D) * K + k) * SGB, es + gid * V + 2 * tig, rows, gid, tig, xa);
 #pragma unroll
             for (int nt = 0; nt < NTn; ++nt)
 #pragma unroll
@@ -267,9 +268,9 @@ graph_agg_dy_mma_kernel(SgP p, Opnd go, const float* __restrict__ A, bf16* __res
     constexpr int NTn = SgCfg<V>::NTn, SGB = SgCfg<V>::SGB;
     extern __shared__ __align__(16) unsigned char sg_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
-    unsigned char* my = sg_smem + (size_t)warp * 5 * SGB;                    // [2][P, Q] input blocks + 1 output block
+    unsigned char* my = sg_smem + (size_t)warp * (2 * SG_D + 1) * SGB;       // [SG_D][P, Q] input blocks + 1 output block
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
-    unsigned char* obuf = my + 4 * SGB;
+    unsigned char* obuf = my + 2 * SG_D * SGB;
     // B fragments: B[k = w][n = v] = A_k[v][w], pairs along w
     uint32_t bq[K][2][NTn][2];
 #pragma unroll
@@ -303,19 +304,19 @@ graph_agg_dy_mma_kernel(SgP p, Opnd go, const float* __restrict__ A, bf16* __res
     auto stage = [&](long long j) {
         if (j < J) {
             const int rows = min(16, p.T - s_tb * 16);
-            const int o = (int)(j & 1) * 2 * SGB;
+            const int o = (int)(j % SG_D) * 2 * SGB;
             sg_stage(my_s + o, my + o, src_of(go.p, go.pns, s_unit, s_tb), rows * V * 2, pbeg, pend, lane);
             if (has_q) sg_stage(my_s + o + SGB, my + o + SGB, src_of(go.q, go.qns, s_unit, s_tb), rows * V * 2, qbeg, qend, lane);
             if (++s_tb == p.nblk) { s_tb = 0; s_unit += wstride; }
         }
         sg_commit();
     };
-    stage(0);
+    for (int d = 0; d < SG_D - 1; ++d) stage(d);
     int unit = wg, tb = 0;
     OpCoef cf = {1.f, 0.f, 0.f};
     for (long long j = 0; j < J; ++j) {
-        stage(j + 1);
-        sg_wait<1>();
+        stage(j + SG_D - 1);
+        sg_wait<SG_D - 1>();
         __syncwarp();
         const int rows = min(16, p.T - tb * 16);
         const int n = unit / p.C, c = unit - n * p.C;
@@ -324,7 +325,7 @@ graph_agg_dy_mma_kernel(SgP p, Opnd go, const float* __restrict__ A, bf16* __res
         const int esp = (int)(reinterpret_cast<uintptr_t>(sp) & 15) >> 1;
         int esq = 0;
         if (has_q) esq = (int)(reinterpret_cast<uintptr_t>(src_of(go.q, go.qns, unit, tb)) & 15) >> 1;
-        const unsigned char* bp = my + (int)(j & 1) * 2 * SGB;
+        const unsigned char* bp = my + (int)(j % SG_D) * 2 * SGB;
         uint32_t ga[2][4];
         sg_frags_lazy<V>(bp, bp + SGB, esp + gid * V + 2 * tig, esq + gid * V + 2 * tig, rows, gid, tig, cf, has_q, go.relu != 0, plain, ga);
 #pragma unroll
@@ -360,7 +361,7 @@ graph_agg_dA_mma_kernel(SgP p, Opnd go, const bf16* __restrict__ y, float* __res
     extern __shared__ __align__(16) unsigned char sg_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
     float* dAs = reinterpret_cast<float*>(sg_smem);                          // [V*V] CTA accumulator
-    unsigned char* my = sg_smem + ((V * V * 4 + 15) & ~15) + (size_t)warp * 6 * SGB;      // [2][y, P, Q]
+    unsigned char* my = sg_smem + ((V * V * 4 + 15) & ~15) + (size_t)warp * 3 * SG_D * SGB;      // [SG_D][y, P, Q]
     const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
     for (int i = threadIdx.x; i < V * V; i += SG_THREADS) dAs[i] = 0.f;
     __syncthreads();
@@ -385,7 +386,7 @@ graph_agg_dA_mma_kernel(SgP p, Opnd go, const bf16* __restrict__ y, float* __res
     auto stage = [&](long long j) {
         if (j < J) {
             const int rows = min(16, p.T - s_tb * 16);
-            const int o = (int)(j & 1) * 3 * SGB;
+            const int o = (int)(j % SG_D) * 3 * SGB;
             sg_stage(my_s + o, my + o, src_of(y, p.yns, (long long)k * p.C, s_unit, s_tb), rows * V * 2, ybeg, yend, lane);
             sg_stage(my_s + o + SGB, my + o + SGB, src_of(go.p, go.pns, 0, s_unit, s_tb), rows * V * 2, pbeg, pend, lane);
             if (has_q) sg_stage(my_s + o + 2 * SGB, my + o + 2 * SGB, src_of(go.q, go.qns, 0, s_unit, s_tb), rows * V * 2, qbeg, qend, lane);
@@ -393,7 +394,7 @@ graph_agg_dA_mma_kernel(SgP p, Opnd go, const bf16* __restrict__ y, float* __res
         }
         sg_commit();
     };
-    stage(0);
+    for (int d = 0; d < SG_D - 1; ++d) stage(d);
     int unit = wg, tb = 0;
     OpCoef cf = {1.f, 0.f, 0.f};
     float acc[2][NTn][4];                                // dA_k[v = 16 mu + ...][w = 8 nt + ...]
@@ -402,13 +403,13 @@ graph_agg_dA_mma_kernel(SgP p, Opnd go, const bf16* __restrict__ y, float* __res
 #pragma unroll
         for (int nt = 0; nt < NTn; ++nt) acc[mu][nt][0] = acc[mu][nt][1] = acc[mu][nt][2] = acc[mu][nt][3] = 0.f;
     for (long long j = 0; j < J; ++j) {
-        stage(j + 1);
-        sg_wait<1>();
+        stage(j + SG_D - 1);
+        sg_wait<SG_D - 1>();
         __syncwarp();
         const int rows = min(16, p.T - tb * 16);
         const int c = unit % p.C;
         if (tb == 0) cf = opnd_coef(go, c);
-        const unsigned char* bb = my + (int)(j & 1) * 3 * SGB;
+        const unsigned char* bb = my + (int)(j % SG_D) * 3 * SGB;
         const int esy = (int)(reinterpret_cast<uintptr_t>(src_of(y, p.yns, (long long)k * p.C, unit, tb)) & 15) >> 1;
         const int esp = (int)(reinterpret_cast<uintptr_t>(src_of(go.p, go.pns, 0, unit, tb)) & 15) >> 1;
         int esq = 0;
@@ -464,7 +465,7 @@ int graph_agg_fwd_mma(int N, int K, int C, int T, int V, const void* y, long lon
     if ((reinterpret_cast<uintptr_t>(y) & 1) || (reinterpret_cast<uintptr_t>(out) & 1)) return 0;
     SgP p = {N, K, C, T, yns, ons, N * C, (T + 15) / 16};
     const size_t sgb = V == 20 ? SgCfg<20>::SGB : SgCfg<25>::SGB;
-    const size_t sm = (size_t)SG_WARPS * (2 * K + 1) * sgb;
+    const size_t sm = (size_t)SG_WARPS * (SG_D * K + 1) * sgb;
     const int grid = sg_grid(p, sm);
 #define SG_FWD(VV, KK)                                                                                                 \
     do {                                                                                                                \
@@ -489,7 +490,7 @@ int graph_agg_bwd_mma(int N, int K, int C, int T, int V, const Opnd& go, const v
     SgP p = {N, K, C, T, yns, dyns, N * C, (T + 15) / 16};
     const size_t sgb = V == 20 ? SgCfg<20>::SGB : SgCfg<25>::SGB;
     if (dy) {
-        const size_t sm = (size_t)SG_WARPS * 5 * sgb;
+        const size_t sm = (size_t)SG_WARPS * (2 * SG_D + 1) * sgb;
         const int grid = sg_grid(p, sm);
 #define SG_DY(VV, KK)                                                                                                  \
     do {                                                                                                                \
@@ -504,7 +505,7 @@ int graph_agg_bwd_mma(int N, int K, int C, int T, int V, const Opnd& go, const v
         if (check_launch("graph_agg_bwd(dy, mma)") < 0) return -2;
     }
     if (dA) {
-        const size_t sm = (size_t)((V * V * 4 + 15) & ~15) + (size_t)SG_WARPS * 6 * sgb;
+        const size_t sm = (size_t)((V * V * 4 + 15) & ~15) + (size_t)SG_WARPS * 3 * SG_D * sgb;
         int gx = sg_grid(p, sm) / K;
         if (gx < 1) gx = 1;
         dim3 grid(gx, K);
